@@ -1,0 +1,339 @@
+"""ctypes view of the CPU ORACLE (oracle/sublinear_oracle.c) — test infrastructure, NOT product code.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  It restates the reference's Rust CPU path (see sublinear_oracle.h for the citations);
+the reference itself (Rust/TypeScript) cannot be built in this image, so there is no oracle/_ref.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+OK = 0
+ERR_NOT_DIAGONALLY_DOMINANT = 1
+ERR_NUMERICAL_INSTABILITY = 2
+ERR_CONVERGENCE_FAILURE = 3
+ERR_INVALID_INPUT = 4
+ERR_DIMENSION_MISMATCH = 5
+ERR_INDEX_OUT_OF_BOUNDS = 8
+ERR_INVALID_SPARSE_MATRIX = 9
+
+MODE_CORRECT, MODE_REF_COMPAT = 0, 1
+DOM_ROW, DOM_ROW_OR_COL = 0, 1
+SPMV_SCALAR, SPMV_SIMD4, SPMV_PARALLEL = 0, 1, 2
+
+
+class _Csr(C.Structure):
+    _fields_ = [("nrows", C.c_uint64), ("ncols", C.c_uint64), ("nnz", C.c_uint64),
+                ("values", C.POINTER(C.c_double)), ("col_indices", C.POINTER(C.c_uint32)),
+                ("row_ptr", C.POINTER(C.c_uint32))]
+
+
+class _Options(C.Structure):
+    _fields_ = [("tolerance", C.c_double), ("max_iterations", C.c_uint64),
+                ("initial_guess", C.POINTER(C.c_double)), ("initial_guess_len", C.c_uint64),
+                ("compute_error_bounds", C.c_int), ("max_terms", C.c_uint64),
+                ("series_tolerance", C.c_double), ("adaptive_truncation", C.c_int),
+                ("mode", C.c_int), ("dominance", C.c_int), ("spmv_variant", C.c_int),
+                ("nthreads", C.c_int)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("solution", C.POINTER(C.c_double)), ("residual_norm", C.c_double),
+                ("iterations", C.c_uint64), ("terms_computed", C.c_uint64),
+                ("matvec_count", C.c_uint64), ("converged", C.c_int), ("series_converged", C.c_int),
+                ("has_error_bound", C.c_int), ("error_bound", C.c_double),
+                ("last_term_norm", C.c_double), ("total_time_ms", C.c_double)]
+
+
+def build(fast: bool = False, out_dir: str | None = None) -> str:
+    """Compile the oracle with the system gcc (the image's $CC wrapper lacks libgomp)."""
+    name = "liboracle_fast.so" if fast else "liboracle.so"
+    out = os.path.join(out_dir or _HERE, name)
+    src = os.path.join(_HERE, "sublinear_oracle.c")
+    hdr = os.path.join(_HERE, "sublinear_oracle.h")
+    if os.path.exists(out) and out_dir is None and \
+            os.path.getmtime(out) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return out
+    opt = ["-O3", "-march=native"] if fast else ["-O2"]
+    cmd = ["/usr/bin/gcc", *opt, "-std=c11", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off",
+           "-o", out, src, "-lm"]
+    subprocess.run(cmd, check=True)
+    return out
+
+
+_libs: dict = {}
+
+
+def lib(fast: bool = False, out_dir: str | None = None):
+    key = (fast, out_dir)
+    if key in _libs:
+        return _libs[key]
+    L = C.CDLL(build(fast, out_dir))
+    u64p, f64p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_double), C.POINTER(C.c_uint32)
+    L.orc_csr_free.argtypes = [C.POINTER(_Csr)]
+    L.orc_csr_free.restype = None
+    L.orc_csr_from_triplets.argtypes = [u64p, u64p, f64p, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(_Csr)]
+    L.orc_csr_get.argtypes = [C.POINTER(_Csr), C.c_uint64, C.c_uint64, f64p]
+    for f in (L.orc_spmv_scalar, L.orc_spmv_simd4):
+        f.argtypes = [C.POINTER(_Csr), f64p, f64p]
+        f.restype = None
+    L.orc_spmv_parallel.argtypes = [C.POINTER(_Csr), f64p, f64p, C.c_int]
+    L.orc_spmv_parallel.restype = None
+    L.orc_multiply_vector.argtypes = [C.POINTER(_Csr), f64p, C.c_uint64, f64p, C.c_uint64, C.c_int, C.c_int]
+    L.orc_is_diagonally_dominant.argtypes = [C.POINTER(_Csr), u64p]
+    L.orc_is_col_diagonally_dominant.argtypes = [C.POINTER(_Csr)]
+    for f in (L.orc_l2_norm, L.orc_l1_norm, L.orc_linf_norm):
+        f.argtypes = [f64p, C.c_uint64]
+        f.restype = C.c_double
+    L.orc_dot_simd4.argtypes = [f64p, f64p, C.c_uint64]
+    L.orc_dot_simd4.restype = C.c_double
+    L.orc_axpy_simd4.argtypes = [C.c_double, f64p, f64p, C.c_uint64]
+    L.orc_axpy_simd4.restype = None
+    L.orc_options_default.argtypes = [C.POINTER(_Options)]
+    L.orc_options_default.restype = None
+    L.orc_neumann_solve.argtypes = [C.POINTER(_Csr), f64p, C.c_uint64, C.POINTER(_Options), C.POINTER(_Result)]
+    L.orc_push_iterations.argtypes = [C.POINTER(_Csr), f64p, C.c_uint64, C.c_int, C.c_int, f64p, f64p, f64p]
+    L.orc_push_iterations.restype = C.c_double
+    L.orc_gen_bench_k.argtypes = [C.c_uint64, C.c_double]
+    L.orc_gen_bench_k.restype = C.c_uint64
+    L.orc_gen_bench_csr.argtypes = [C.c_uint64, C.c_double, C.c_uint64, C.c_uint64, C.POINTER(_Csr), f64p]
+    L.orc_gen_bench_triplets.argtypes = [C.c_uint64, C.c_double, u64p, u64p, f64p, C.c_uint64]
+    L.orc_gen_bench_triplets.restype = C.c_int64
+    L.orc_gen_ultra_triplets.argtypes = [C.c_uint64, C.c_double, u64p, u64p, f64p, C.c_uint64]
+    L.orc_gen_ultra_triplets.restype = C.c_int64
+    L.orc_pagerank_system.argtypes = [u64p, u64p, f64p, C.c_uint64, C.c_uint64, C.c_double, C.POINTER(_Csr), f64p]
+    L.orc_solve_entry.argtypes = [C.POINTER(_Csr), f64p, u64p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, f64p, f64p]
+    L.orc_ts_lcg_next.argtypes = [C.c_uint32, f64p]
+    L.orc_ts_lcg_next.restype = C.c_uint32
+    _libs[key] = L
+    return L
+
+
+class OracleError(Exception):
+    def __init__(self, code: int, what: str = ""):
+        super().__init__(f"oracle error code {code} {what}")
+        self.code = code
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+class Csr:
+    """CSRStorage restated (values f64 / col_indices u32 / row_ptr u32), numpy-backed."""
+
+    def __init__(self, nrows, ncols, values, col_indices, row_ptr):
+        self.nrows, self.ncols = int(nrows), int(ncols)
+        self.values = _f64(values)
+        self.col_indices = np.ascontiguousarray(col_indices, dtype=np.uint32)
+        self.row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint32)
+        assert self.row_ptr.shape[0] == self.nrows + 1
+        self.nnz = int(self.values.shape[0])
+
+    def c(self) -> _Csr:
+        return _Csr(self.nrows, self.ncols, self.nnz, _p(self.values, C.c_double),
+                    _p(self.col_indices, C.c_uint32), _p(self.row_ptr, C.c_uint32))
+
+    @staticmethod
+    def _take(raw: _Csr, L) -> "Csr":
+        nnz, n = int(raw.nnz), int(raw.nrows)
+        vals = np.ctypeslib.as_array(raw.values, shape=(max(nnz, 1),))[:nnz].copy()
+        cols = np.ctypeslib.as_array(raw.col_indices, shape=(max(nnz, 1),))[:nnz].copy()
+        rp = np.ctypeslib.as_array(raw.row_ptr, shape=(n + 1,)).copy()
+        out = Csr(n, int(raw.ncols), vals, cols, rp)
+        L.orc_csr_free(C.byref(raw))
+        return out
+
+    @staticmethod
+    def from_triplets(rows, cols, vals, nrows, ncols) -> "Csr":
+        L = lib()
+        r, c, v = _u64(rows), _u64(cols), _f64(vals)
+        raw = _Csr()
+        rc = L.orc_csr_from_triplets(_p(r, C.c_uint64), _p(c, C.c_uint64), _p(v, C.c_double),
+                                     len(v), nrows, ncols, C.byref(raw))
+        if rc != OK:
+            raise OracleError(rc, "from_triplets")
+        return Csr._take(raw, L)
+
+    @staticmethod
+    def from_dense(a) -> "Csr":
+        """SparseMatrix::from_dense (src/matrix/mod.rs:202-223): row-major scan, zeros filtered."""
+        a = np.asarray(a, dtype=np.float64)
+        r, c = np.nonzero(a)
+        return Csr.from_triplets(r, c, a[r, c], a.shape[0], a.shape[1])
+
+    def get(self, row, col):
+        out = C.c_double()
+        m = self.c()
+        return out.value if lib().orc_csr_get(C.byref(m), row, col, C.byref(out)) else None
+
+    def multiply_vector(self, x, variant=SPMV_SCALAR, nthreads=0, ylen=None):
+        x = _f64(x)
+        y = np.zeros(self.nrows if ylen is None else ylen)
+        m = self.c()
+        rc = lib().orc_multiply_vector(C.byref(m), _p(x, C.c_double), len(x), _p(y, C.c_double), len(y),
+                                       variant, nthreads)
+        if rc != OK:
+            raise OracleError(rc, "multiply_vector")
+        return y
+
+    def is_diagonally_dominant(self):
+        m = self.c()
+        bad = C.c_uint64()
+        return bool(lib().orc_is_diagonally_dominant(C.byref(m), C.byref(bad)))
+
+    def first_non_dominant_row(self):
+        m = self.c()
+        bad = C.c_uint64()
+        lib().orc_is_diagonally_dominant(C.byref(m), C.byref(bad))
+        return None if bad.value == 2 ** 64 - 1 else bad.value
+
+    def is_col_diagonally_dominant(self):
+        m = self.c()
+        return bool(lib().orc_is_col_diagonally_dominant(C.byref(m)))
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.values, self.col_indices.astype(np.int64), self.row_ptr.astype(np.int64)),
+                             shape=(self.nrows, self.ncols))
+
+
+@dataclass
+class Result:
+    solution: np.ndarray
+    residual_norm: float
+    iterations: int
+    terms_computed: int
+    matvec_count: int
+    converged: bool
+    series_converged: bool
+    error_bound: float | None
+    last_term_norm: float
+    total_time_ms: float
+    status: int = OK
+
+
+def neumann_solve(m: Csr, b, *, tolerance=1e-6, max_iterations=1000, initial_guess=None,
+                  compute_error_bounds=False, max_terms=50, series_tolerance=1e-8,
+                  adaptive_truncation=True, mode=MODE_CORRECT, dominance=DOM_ROW,
+                  spmv_variant=SPMV_SCALAR, nthreads=0, fast=False, raise_on_error=True) -> Result:
+    L = lib(fast)
+    b = _f64(b)
+    o = _Options()
+    L.orc_options_default(C.byref(o))
+    o.tolerance, o.max_iterations = tolerance, max_iterations
+    o.compute_error_bounds, o.max_terms = int(compute_error_bounds), max_terms
+    o.series_tolerance, o.adaptive_truncation = series_tolerance, int(adaptive_truncation)
+    o.mode, o.dominance, o.spmv_variant, o.nthreads = mode, dominance, spmv_variant, nthreads
+    ig = None
+    if initial_guess is not None:
+        ig = _f64(initial_guess)
+        o.initial_guess, o.initial_guess_len = _p(ig, C.c_double), len(ig)
+    x = np.zeros(m.nrows)
+    r = _Result()
+    r.solution = _p(x, C.c_double)
+    mc = m.c()
+    rc = L.orc_neumann_solve(C.byref(mc), _p(b, C.c_double), len(b), C.byref(o), C.byref(r))
+    if rc != OK and (raise_on_error or rc not in (ERR_CONVERGENCE_FAILURE, ERR_NUMERICAL_INSTABILITY)):
+        raise OracleError(rc, "neumann_solve")
+    return Result(x, r.residual_norm, int(r.iterations), int(r.terms_computed), int(r.matvec_count),
+                  bool(r.converged), bool(r.series_converged),
+                  r.error_bound if r.has_error_bound else None, r.last_term_norm, r.total_time_ms, rc)
+
+
+def push_iterations(m: Csr, b, nterms, spmv_variant=SPMV_SCALAR, nthreads=0, fast=False):
+    """x, t, per-term norms and seconds for `nterms` bare push iterations after term 0."""
+    L = lib(fast)
+    b = _f64(b)
+    x, t, norms = np.zeros(m.nrows), np.zeros(m.nrows), np.zeros(max(nterms, 1))
+    mc = m.c()
+    secs = L.orc_push_iterations(C.byref(mc), _p(b, C.c_double), nterms, spmv_variant, nthreads,
+                                 _p(x, C.c_double), _p(t, C.c_double), _p(norms, C.c_double))
+    return x, t, norms[:nterms], secs
+
+
+def gen_bench_k(size, sparsity):
+    return int(lib().orc_gen_bench_k(size, sparsity))
+
+
+def gen_bench_csr(size, sparsity, row0=0, row1=None, fast=False):
+    """create_test_matrix/create_test_rhs (benches/performance_benchmarks.rs:12-43), rows [row0,row1)."""
+    L = lib(fast)
+    row1 = size if row1 is None else row1
+    raw = _Csr()
+    b = np.zeros(row1 - row0)
+    rc = L.orc_gen_bench_csr(size, sparsity, row0, row1, C.byref(raw), _p(b, C.c_double))
+    if rc != OK:
+        raise OracleError(rc, "gen_bench_csr")
+    return Csr._take(raw, L), b
+
+
+def gen_bench_triplets(size, sparsity):
+    L = lib()
+    cap = size * gen_bench_k(size, sparsity) + 1
+    r, c, v = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64), np.zeros(cap)
+    n = L.orc_gen_bench_triplets(size, sparsity, _p(r, C.c_uint64), _p(c, C.c_uint64), _p(v, C.c_double), cap)
+    assert n >= 0
+    b = 1.0 + np.arange(size, dtype=np.float64) * 0.001
+    return r[:n], c[:n], v[:n], b
+
+
+def gen_ultra_triplets(size, sparsity):
+    L = lib()
+    cap = size * 11 + 1
+    r, c, v = np.zeros(cap, np.uint64), np.zeros(cap, np.uint64), np.zeros(cap)
+    n = L.orc_gen_ultra_triplets(size, sparsity, _p(r, C.c_uint64), _p(c, C.c_uint64), _p(v, C.c_double), cap)
+    assert n >= 0
+    return r[:n], c[:n], v[:n], np.ones(size)
+
+
+def pagerank_system(src, dst, n, alpha=0.85, weights=None):
+    L = lib()
+    s, d = _u64(src), _u64(dst)
+    w = None if weights is None else _f64(weights)
+    raw = _Csr()
+    rhs = np.zeros(n)
+    rc = L.orc_pagerank_system(_p(s, C.c_uint64), _p(d, C.c_uint64),
+                               None if w is None else _p(w, C.c_double), len(s), n, alpha,
+                               C.byref(raw), _p(rhs, C.c_double))
+    if rc != OK:
+        raise OracleError(rc, "pagerank_system")
+    return Csr._take(raw, L), rhs
+
+
+def solve_entry(m: Csr, b, rows, nwalks, max_steps=1000, seed=0):
+    L = lib()
+    b, q = _f64(b), _u64(rows)
+    est, var = np.zeros(len(q)), np.zeros(len(q))
+    mc = m.c()
+    rc = L.orc_solve_entry(C.byref(mc), _p(b, C.c_double), _p(q, C.c_uint64), len(q), nwalks, max_steps, seed,
+                           _p(est, C.c_double), _p(var, C.c_double))
+    if rc != OK:
+        raise OracleError(rc, "solve_entry")
+    return est, var
+
+
+def ts_lcg(seed, count):
+    """createSeededRandom (src/core/utils.ts:161-168) stream."""
+    L = lib()
+    s, out = C.c_uint32(seed & 0xFFFFFFFF).value, []
+    for _ in range(count):
+        u = C.c_double()
+        s = L.orc_ts_lcg_next(s, C.byref(u))
+        out.append(u.value)
+    return out
