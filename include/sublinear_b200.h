@@ -1,0 +1,277 @@
+/*
+ * sublinear_b200.h — C ABI of the B200-native Neumann-series / push-iteration path.
+ *
+ * This is the drop-in boundary for ONE hot path of ruvnet/sublinear-time-solver: what a Rust
+ * `extern "C"` block (or cgo / ctypes / N-API) binds in place of the crate's CPU implementation of
+ *   SparseMatrix::from_triplets / Matrix::multiply_vector        (src/matrix/mod.rs:160-199, 415-439)
+ *   NeumannSolver::{new,default,fast,high_precision,solve}        (src/solver/neumann.rs:36-80, 469-555)
+ *   SolverOptions / SolverResult / SolverError                    (src/solver/mod.rs:22-195, src/error.rs:16-138)
+ * plus the entry-estimation and PageRank front doors that only exist in the TS package
+ *   SublinearSolver.estimateEntry / computePageRank               (src/core/solver.ts:550-659, 664-722).
+ * The reference has no C FFI of its own; its only FFI is wasm-bindgen (src/wasm_iface.rs:45-243), whose
+ * handle lifecycle (new ... dispose) and flat-slice arguments this header follows.
+ *
+ * Conventions
+ *  - plain pointers + sizes, no C++/torch types; every function returns int32_t: 0 or an SB200_ERR_* code
+ *    equal to the 1-based position of the variant in `enum SolverError` (src/error.rs:16-138);
+ *    sb200_last_error() returns the message of the calling thread's last failure.
+ *  - all pointers are caller-owned HOST pointers unless the name ends in `_dev` (device pointers on the
+ *    handle's GPU) ; sb200_result.solution is library-owned until sb200_result_free().
+ *  - the matrix handle owns a device-resident CSR copy (values f64 / col_indices u32 / row_ptr u32 —
+ *    CSRStorage, src/matrix/sparse.rs:16-23); solve calls are re-entrant on one handle, like
+ *    `solve(&self, &dyn Matrix, ..)` in the reference (workspaces are per call).
+ *  - there is no CPU fallback: every compute entry point fails with SB200_ERR_ALGORITHM if no CUDA device
+ *    is usable.
+ */
+#ifndef SUBLINEAR_B200_H
+#define SUBLINEAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_ABI_VERSION 1
+
+/* SolverError variants (src/error.rs:16-138), 1-based in declaration order. */
+typedef enum sb200_status {
+    SB200_OK = 0,
+    SB200_ERR_MATRIX_NOT_DIAGONALLY_DOMINANT = 1,
+    SB200_ERR_NUMERICAL_INSTABILITY = 2,
+    SB200_ERR_CONVERGENCE_FAILURE = 3,
+    SB200_ERR_INVALID_INPUT = 4,
+    SB200_ERR_DIMENSION_MISMATCH = 5,
+    SB200_ERR_UNSUPPORTED_MATRIX_FORMAT = 6,
+    SB200_ERR_MEMORY_ALLOCATION = 7,
+    SB200_ERR_INDEX_OUT_OF_BOUNDS = 8,
+    SB200_ERR_INVALID_SPARSE_MATRIX = 9,
+    SB200_ERR_ALGORITHM = 10,      /* also: CUDA / NCCL failures, missing device */
+    SB200_ERR_WASM_BINDING = 11,   /* never produced; kept so codes line up with the enum */
+    SB200_ERR_IO = 12,
+    SB200_ERR_SERIALIZATION = 13
+} sb200_status;
+
+/* ConvergenceMode / NormType (src/types.rs:30-55). The Neumann loop itself only uses the L2 residual
+ * (src/solver/neumann.rs:316, 422-430); the fields are carried for API fidelity. */
+enum { SB200_CONV_RESIDUAL_NORM = 0, SB200_CONV_RELATIVE_RESIDUAL = 1, SB200_CONV_SOLUTION_CHANGE = 2,
+       SB200_CONV_RELATIVE_SOLUTION_CHANGE = 3, SB200_CONV_COMBINED = 4 };
+enum { SB200_NORM_L1 = 0, SB200_NORM_L2 = 1, SB200_NORM_LINF = 2, SB200_NORM_WEIGHTED = 3 };
+
+/* Which semantics sb200_solve follows. */
+enum {
+    SB200_MODE_CORRECT = 0,    /* x = sum_k (-D^-1 R)^k D^-1 b ; residual = ||A x - b||_2 (the documented maths) */
+    SB200_MODE_REF_COMPAT = 1  /* literal neumann.rs control flow incl. its quirks: x starts at D^-1 b, residual vs D^-1 b */
+};
+/* Dominance accepted by the solver: Rust checks rows only (src/matrix/mod.rs:467-485); the TS analyser
+ * accepts row OR column dominance (src/core/matrix.ts:343-345), which PageRank systems need. */
+enum { SB200_DOMINANCE_ROW = 0, SB200_DOMINANCE_ROW_OR_COL = 1 };
+/* Residual cadence: the reference recomputes ||A x - rhs|| every 5th iteration (neumann.rs:489-491);
+ * IDENTITY takes ||b - A x_k|| = ||D o t_{k+1}|| from the push kernel for free (SURVEY.md F12;
+ * MODE_CORRECT only) and runs one verifying residual SpMV at the end. */
+enum { SB200_RESIDUAL_EVERY_5 = 0, SB200_RESIDUAL_IDENTITY = 1 };
+/* Duplicate (row,col) policy at ingest: Rust keeps them as separate entries. */
+enum { SB200_DUP_KEEP = 0, SB200_DUP_SUM = 1 };
+
+typedef struct sb200_matrix sb200_matrix; /* SparseMatrix in CSR form, device resident */
+typedef struct sb200_solver sb200_solver; /* NeumannSolver configuration */
+typedef struct sb200_comm sb200_comm;     /* one rank of a row-partitioned multi-GPU job */
+
+/* SolverOptions (src/solver/mod.rs:22-45) as a POD, followed by this library's extensions. */
+typedef struct sb200_options {
+    double tolerance;              /* 1e-6  */
+    uint64_t max_iterations;       /* 1000  */
+    int32_t convergence_mode;      /* SB200_CONV_RESIDUAL_NORM */
+    int32_t norm_type;             /* SB200_NORM_L2 */
+    int32_t collect_stats;         /* 0 */
+    uint64_t streaming_interval;   /* 0 (carried, unused by NeumannSolver::solve) */
+    const double *initial_guess;   /* NULL = None */
+    uint64_t initial_guess_len;
+    int32_t compute_error_bounds;  /* 0 */
+    double error_bounds_tolerance; /* 1e-8 */
+    int32_t enable_profiling;      /* 0 */
+    int32_t has_random_seed;       /* 0 = None */
+    uint64_t random_seed;
+    /* extensions */
+    int32_t mode;                  /* SB200_MODE_CORRECT */
+    int32_t dominance;             /* SB200_DOMINANCE_ROW */
+    int32_t residual_check;        /* SB200_RESIDUAL_EVERY_5 */
+    int32_t reserved;
+} sb200_options;
+
+/* SolverResult (src/solver/mod.rs:121-138) + SolverStats / ErrorBounds / MemoryInfo fields the path fills. */
+typedef struct sb200_result {
+    double *solution;              /* library-owned, solution_len doubles (NULL for *_dev solves) */
+    uint64_t solution_len;
+    double residual_norm;
+    uint64_t iterations;
+    int32_t converged;
+    int32_t has_error_bounds;      /* ErrorBounds::upper_bound_only (neumann.rs:340-343) */
+    double error_upper_bound;
+    int32_t has_stats;             /* SolverStats when options.collect_stats (neumann.rs:539-548) */
+    double total_time_ms;
+    uint64_t matvec_count;
+    uint64_t memory_bytes;         /* MemoryInfo.current_usage_bytes: device bytes of the per-solve workspace */
+    /* extensions */
+    uint64_t terms_computed;
+    int32_t series_converged;
+    double last_term_norm;
+    double device_time_ms;         /* CUDA-event time of the iteration loop (kernels only) */
+    uint64_t kernel_launches;      /* launches of this library's kernels during the call */
+    uint64_t h2d_bytes, d2h_bytes; /* bytes moved across PCIe during the call */
+} sb200_result;
+
+/* ---------------------------------------------------------------------------------------------- */
+/* runtime                                                                                        */
+/* ---------------------------------------------------------------------------------------------- */
+int32_t sb200_abi_version(void);
+size_t sb200_last_error(char *buf, size_t cap);
+int32_t sb200_device_count(int32_t *count);
+/* Device used by handles created afterwards on the calling thread (default 0 or $SUBLINEAR_B200_DEVICE). */
+int32_t sb200_set_device(int32_t device);
+int32_t sb200_get_device(int32_t *device);
+/* Pinned host memory for callers that want PCIe line rate on sb200_solve's b / solution buffers.
+ * Pageable pointers are accepted everywhere and staged through an internal pinned ring. */
+int32_t sb200_host_alloc(uint64_t bytes, void **out);
+int32_t sb200_host_free(void *ptr);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* SparseMatrix                                                                                   */
+/* ---------------------------------------------------------------------------------------------- */
+/* SparseMatrix::from_triplets (src/matrix/mod.rs:160-199): bounds + finiteness validation in triplet
+ * order, exact zeros dropped (sparse.rs:535-541), stable sort by (row,col), duplicates kept (sparse.rs:95). */
+int32_t sb200_matrix_from_triplets(const uint64_t *rows, const uint64_t *cols, const double *vals,
+                                   uint64_t ntriplets, uint64_t nrows, uint64_t ncols, sb200_matrix **out);
+int32_t sb200_matrix_from_triplets_ex(const uint64_t *rows, const uint64_t *cols, const double *vals,
+                                      uint64_t ntriplets, uint64_t nrows, uint64_t ncols, int32_t dup_policy,
+                                      sb200_matrix **out);
+/* Ingest the three CSRStorage slices as they are (src/matrix/sparse.rs:16-23; the 5-slice kernel signature of
+ * src/simd_ops.rs:20-26). Validates monotone row_ptr, column bounds and finite values; rows need not be sorted. */
+int32_t sb200_matrix_from_csr(const uint32_t *row_ptr, const uint32_t *col_indices, const double *values,
+                              uint64_t nrows, uint64_t ncols, uint64_t nnz, sb200_matrix **out);
+int32_t sb200_matrix_from_csr64(const uint64_t *row_ptr, const uint32_t *col_indices, const double *values,
+                                uint64_t nrows, uint64_t ncols, uint64_t nnz, sb200_matrix **out);
+/* SparseMatrix::from_dense / identity / diagonal (src/matrix/mod.rs:202-239). */
+int32_t sb200_matrix_from_dense(const double *data, uint64_t nrows, uint64_t ncols, sb200_matrix **out);
+int32_t sb200_matrix_identity(uint64_t size, sb200_matrix **out);
+int32_t sb200_matrix_diagonal(const double *diag, uint64_t size, sb200_matrix **out);
+void sb200_matrix_free(sb200_matrix *m);
+
+/* Matrix::rows / cols / nnz / get / is_diagonally_dominant / diagonal_dominance_factor (src/matrix/mod.rs:25-104). */
+int32_t sb200_matrix_rows(const sb200_matrix *m, uint64_t *out);
+int32_t sb200_matrix_cols(const sb200_matrix *m, uint64_t *out);
+int32_t sb200_matrix_nnz(const sb200_matrix *m, uint64_t *out);
+int32_t sb200_matrix_get(const sb200_matrix *m, uint64_t row, uint64_t col, double *value, int32_t *present);
+int32_t sb200_matrix_is_diagonally_dominant(const sb200_matrix *m, int32_t dominance, int32_t *out);
+int32_t sb200_matrix_diagonal_dominance_factor(const sb200_matrix *m, double *factor, int32_t *present);
+/* CSRStorage::to_triplets / SparseMatrix::as_csr (src/matrix/sparse.rs:210-227, mod.rs:313-319): copy out.
+ * Any output pointer may be NULL. row_ptr has nrows+1 entries. */
+int32_t sb200_matrix_export_csr(const sb200_matrix *m, uint64_t *row_ptr, uint32_t *col_indices, double *values);
+/* Matrix::multiply_vector / multiply_vector_add (src/matrix/mod.rs:415-465): y = A x, y += A x. */
+int32_t sb200_matrix_multiply_vector(const sb200_matrix *m, const double *x, uint64_t xlen, double *y, uint64_t ylen);
+int32_t sb200_matrix_multiply_vector_add(const sb200_matrix *m, const double *x, uint64_t xlen, double *y, uint64_t ylen);
+/* Same on device pointers, enqueued on `stream` (a cudaStream_t, NULL = default stream); no host sync. */
+int32_t sb200_matrix_multiply_vector_dev(const sb200_matrix *m, const double *x_dev, uint64_t xlen, double *y_dev,
+                                         uint64_t ylen, int32_t accumulate, void *stream);
+/* SparseMatrix::scale / add_diagonal (src/matrix/mod.rs:345-372). */
+int32_t sb200_matrix_scale(sb200_matrix *m, double factor);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* NeumannSolver + SolverOptions                                                                  */
+/* ---------------------------------------------------------------------------------------------- */
+/* NeumannSolver::new(max_terms, series_tolerance) / default() / high_precision() / fast() (neumann.rs:48-80). */
+int32_t sb200_neumann_new(uint64_t max_terms, double series_tolerance, sb200_solver **out);
+int32_t sb200_neumann_default(sb200_solver **out);
+int32_t sb200_neumann_high_precision(sb200_solver **out);
+int32_t sb200_neumann_fast(sb200_solver **out);
+/* with_adaptive_truncation / with_power_caching (neumann.rs:83-92). */
+int32_t sb200_neumann_with_adaptive_truncation(sb200_solver *s, int32_t enable);
+int32_t sb200_neumann_with_power_caching(sb200_solver *s, int32_t enable);
+int32_t sb200_neumann_config(const sb200_solver *s, uint64_t *max_terms, double *series_tolerance,
+                             int32_t *adaptive_truncation, int32_t *cache_powers);
+/* SolverAlgorithm::algorithm_name (neumann.rs:464-466): "neumann". */
+const char *sb200_solver_algorithm_name(const sb200_solver *s);
+void sb200_solver_free(sb200_solver *s);
+
+/* SolverOptions::default / high_precision / fast / streaming(interval) (src/solver/mod.rs:47-116). */
+void sb200_options_default(sb200_options *o);
+void sb200_options_high_precision(sb200_options *o);
+void sb200_options_fast(sb200_options *o);
+void sb200_options_streaming(sb200_options *o, uint64_t interval);
+
+/* NeumannSolver::solve(&matrix, &b, &options) -> Result<SolverResult> (src/solver/neumann.rs:469-555).
+ * On SB200_ERR_CONVERGENCE_FAILURE / SB200_ERR_NUMERICAL_INSTABILITY `out` is still filled (iterations,
+ * residual_norm = the fields of the Err variant, plus the last iterate). */
+int32_t sb200_solve(const sb200_solver *s, const sb200_matrix *m, const double *b, uint64_t blen,
+                    const sb200_options *opt, sb200_result *out);
+/* Same, writing the solution into a caller buffer of blen doubles (out->solution stays NULL). */
+int32_t sb200_solve_into(const sb200_solver *s, const sb200_matrix *m, const double *b, uint64_t blen,
+                         const sb200_options *opt, double *x_out, sb200_result *out);
+/* Inputs/outputs already resident in HBM: b_dev, x_dev (and opt->initial_guess, if set) are device
+ * pointers on the matrix's GPU; work is enqueued on `stream`; the call returns after the loop finished. */
+int32_t sb200_solve_dev(const sb200_solver *s, const sb200_matrix *m, const double *b_dev, uint64_t blen,
+                        const sb200_options *opt, double *x_dev, void *stream, sb200_result *out);
+void sb200_result_free(sb200_result *r);
+
+/* The bare recurrence, for measurement and per-term parity: from t = D^-1 b, x = t run exactly `nterms`
+ * push iterations t <- t - D^-1 (A t); x += t (neumann.rs:280-299 + 264-266 + 271) with no convergence logic.
+ * Device pointers; x_dev / t_dev / term_norms (host, nterms doubles) may be NULL. elapsed_ms = CUDA-event
+ * time of the nterms kernel launches alone. */
+int32_t sb200_push_iterations_dev(const sb200_matrix *m, const double *b_dev, uint64_t blen, uint64_t nterms,
+                                  double *x_dev, double *t_dev, double *term_norms, void *stream,
+                                  float *elapsed_ms);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* single-entry estimation and PageRank (TS-only front doors)               */
+/* ---------------------------------------------------------------------------------------------- */
+/* Batched estimate of x[rows[q]] for A x = b by absorbing random walks (Ulam-von Neumann estimator,
+ * SURVEY.md Appendix C).  nwalks = 0 -> max(100, ceil(1/eps^2)) (src/core/solver.ts:587);
+ * max_steps = 0 -> 1000 (src/core/solver.ts:399).  est / var: nqueries doubles each (var may be NULL). */
+int32_t sb200_solve_entry(const sb200_matrix *m, const double *b, uint64_t blen, const uint64_t *rows,
+                          uint64_t nqueries, double eps, uint64_t nwalks, uint64_t max_steps, uint64_t seed,
+                          double *est, double *var);
+/* computePageRank's system (src/core/solver.ts:664-722): S = I - alpha P^T with dangling mass dropped,
+ * rhs = (1-alpha)/n.  Edge e: src[e] -> dst[e] with weight w[e] (w NULL = 1). rhs: n doubles (may be NULL). */
+int32_t sb200_pagerank_system(const uint64_t *src, const uint64_t *dst, const double *w, uint64_t nedges,
+                              uint64_t n, double alpha, sb200_matrix **S, double *rhs);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* synthetic inputs (the reference's own generators)                               */
+/* ---------------------------------------------------------------------------------------------- */
+/* create_test_matrix + create_test_rhs (benches/performance_benchmarks.rs:12-43), rows [row0,row1) of the
+ * size x size system, emitted in CSR (= from_triplets of the generated triplets; row_ptr local, 64-bit).
+ * Pass NULL outputs to query sizes: *nnz_out receives the nnz of the row range. */
+int32_t sb200_gen_bench_csr(uint64_t size, double sparsity, uint64_t row0, uint64_t row1, uint64_t *row_ptr,
+                            uint32_t *col_indices, double *values, double *b, uint64_t *nnz_out);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* multi-GPU: contiguous row blocks, one process (rank) per GPU, one exchange per iteration       */
+/* ---------------------------------------------------------------------------------------------- */
+#define SB200_UNIQUE_ID_BYTES 128
+/* Rank 0 creates the id and ships it to the other ranks by any host-side means (torch.distributed
+ * broadcast, MPI, a file); every rank then calls sb200_comm_init on its own GPU. */
+int32_t sb200_comm_unique_id(uint8_t id[SB200_UNIQUE_ID_BYTES]);
+int32_t sb200_comm_init(int32_t rank, int32_t world, const uint8_t id[SB200_UNIQUE_ID_BYTES], int32_t device,
+                        sb200_comm **out);
+void sb200_comm_free(sb200_comm *c);
+/* Row partition used by every rank: rank r owns rows [r*ceil(n/world), min(n,(r+1)*ceil(n/world))) — the
+ * reference's own chunking rule (src/simd_ops.rs:219, src/matrix/optimized.rs:485-517). */
+int32_t sb200_partition_rows(uint64_t nrows, int32_t world, int32_t rank, uint64_t *row0, uint64_t *row1);
+/* The rank's row block [row0,row1) of an n x n system: local row_ptr (64-bit), GLOBAL column indices. */
+int32_t sb200_dist_matrix_from_csr(sb200_comm *c, uint64_t n_global, uint64_t row0, uint64_t row1,
+                                   const uint64_t *row_ptr, const uint32_t *col_indices, const double *values,
+                                   sb200_matrix **out);
+/* Distributed NeumannSolver::solve: b_local / x_local hold the rank's rows only (host pointers). Per term:
+ * fused push kernel on the local rows, then one allgather of the updated term slice + a 1-double allreduce. */
+int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matrix *m_local, const double *b_local,
+                         uint64_t nlocal, const sb200_options *opt, double *x_local, sb200_result *out);
+/* Bare distributed recurrence for measurement (cf. sb200_push_iterations_dev); device pointers, local rows. */
+int32_t sb200_dist_push_iterations_dev(sb200_comm *c, const sb200_matrix *m_local, const double *b_local_dev,
+                                       uint64_t nlocal, uint64_t nterms, double *x_local_dev, double *term_norms,
+                                       float *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUBLINEAR_B200_H */

@@ -1,0 +1,177 @@
+// Internal declarations shared by the translation units of libsublinear_b200.so.
+// Nothing here is part of the ABI (include/sublinear_b200.h is).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sublinear_b200.h"
+
+namespace sb200 {
+
+// ---- error plumbing: SolverError code + message, per thread (no exceptions cross the ABI) --------------
+int32_t fail(int32_t code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+void clear_error();
+
+#define SB_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return ::sb200::fail(_e == cudaErrorMemoryAllocation ? SB200_ERR_MEMORY_ALLOCATION          \
+                                                                 : SB200_ERR_ALGORITHM,                 \
+                                 "CUDA error %s at %s:%d (%s)", cudaGetErrorName(_e), __FILE__, __LINE__, \
+                                 cudaGetErrorString(_e));                                               \
+    } while (0)
+
+#define SB_TRY(expr)                  \
+    do {                              \
+        int32_t _rc = (expr);         \
+        if (_rc != SB200_OK) return _rc; \
+    } while (0)
+
+int current_device();           // device new handles are created on (thread-local, env default)
+int32_t require_device(int dev); // cudaSetDevice + "no CPU fallback" check
+
+// ---- device buffers --------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int32_t alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(SB200_ERR_MEMORY_ALLOCATION, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T),
+                        cudaGetErrorString(e));
+        }
+        n = count;
+        return SB200_OK;
+    }
+};
+
+// host<->device copies that take pageable OR pinned host pointers (pageable staged through a pinned ring)
+int32_t copy_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream);
+int32_t copy_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t stream);
+
+// ---- kernel-side contracts -------------------------------------------------------------------------------
+// Tile table entry: tile t covers rows [desc[t].row0, desc[t+1].row0) and nnz [desc[t].nnz0, desc[t+1].nnz0).
+struct TileDesc {
+    uint32_t row0;
+    uint32_t nnz0;
+};
+
+// Tile geometry (one instantiation of the kernel template each).
+struct TileCfg {
+    int threads;  // CTA size = max rows per tile
+    int cap;      // max nnz staged per tile; a single row above it is a "long row" tile
+};
+constexpr int kNumTileCfgs = 3;
+extern const TileCfg kTileCfgs[kNumTileCfgs];
+int default_tile_cfg();
+
+// Device-resident loop state, mirrors the scalars of NeumannState (src/solver/neumann.rs:97-135) that the
+// control flow of NeumannSolver::solve (:469-555) reads. Updated by the last CTA of each kernel.
+struct LoopCtl {
+    double red[2];       // row-partitioned runs: this rank's partial sums, all-reduced in place
+    double term_norm2;   // ||t_k||_2^2 of the latest term
+    double aux_norm2;    // ||D o t_k||^2 (identity residual)
+    double res_norm2;    // latest ||A x - rhs||_2^2
+    double res_norm;     // sqrt(res_norm2)  (+inf before the first residual, neumann.rs:236)
+    double rhs_norm2;    // ||D^-1 b||^2 (error bounds, neumann.rs:329-331)
+    double tolerance, series_tolerance;
+    uint32_t max_terms, max_iterations;
+    uint32_t alive;      // loop still running
+    uint32_t sconv;      // series_converged
+    uint32_t nonfinite;  // NumericalInstability seen
+    uint32_t terms;      // terms_computed
+    uint32_t iterations;
+    uint32_t ticket;     // last-CTA election
+    uint32_t pad[2];
+};
+
+enum Epilogue { EPI_SPMV = 0, EPI_PUSH = 1, EPI_RESID = 2 };
+
+struct TileKernelArgs {
+    // CSR (device)
+    const double *vals;
+    const uint32_t *cols;
+    const uint32_t *row_ptr;
+    const TileDesc *tiles;
+    uint32_t ntiles;
+    uint32_t nrows;
+    // vectors
+    const double *xin;    // gather source (term / solution / x)
+    const double *xin_own; // value of xin for local row i is xin_own[i] (== xin + row offset when distributed)
+    double *out;          // SPMV: y ; PUSH: new term (indexed by local row)
+    double *sol;          // PUSH: solution (read+write)
+    const double *dinv;   // PUSH
+    const double *rhs;    // RESID: subtracted vector
+    int accumulate;       // SPMV: y += A x
+    // loop control
+    LoopCtl *ctl;         // may be null for SPMV
+    double *partials;     // gridDim doubles (x2 when aux)
+    uint32_t it;          // iteration index this launch belongs to
+    int last_in_iter;     // run end-of-iteration logic in the tail
+    int force;            // ignore ctl->alive (final residual / bare recurrence)
+    int identity_res;     // PUSH: also accumulate ||D o t'||^2
+    int defer_tail;       // distributed: only publish the local sums; a later kernel runs the loop logic
+    double *norm_log;     // optional: norm_log[it] = ||t_it||^2 (bare recurrence)
+};
+
+// launchers (kernels.cu). grid = 0 -> persistent grid sized from occupancy.
+int32_t launch_tile_kernel(int cfg, Epilogue epi, const TileKernelArgs &a, cudaStream_t stream);
+int tile_kernel_max_grid(int cfg, Epilogue epi);
+// setup pass over the CSR (K4): per-row dominance, diagonal and its inverse
+struct SetupOut {
+    double *dinv;                  // n
+    unsigned long long *first_bad_dd;    // first row violating row dominance (or ~0)
+    unsigned long long *first_bad_diag;  // first row with missing / ~zero diagonal (or ~0)
+    double *col_diag, *col_off;    // optional column accumulators (n each) for column dominance
+    double *min_factor_bits;       // optional: min diag/off ratio (as double, atomicMin on ordered bits)
+};
+int32_t launch_setup_rows(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
+                          int compat_diag, SetupOut out, cudaStream_t stream);
+int32_t launch_col_dominance(const double *col_diag, const double *col_off, uint32_t n, unsigned long long *first_bad,
+                             cudaStream_t stream);
+// iteration 0 (neumann.rs:191-211 + first compute_next_term): c = b*dinv; t = c (or (b - Ax0)*dinv); x = base + t
+struct InitArgs {
+    const double *b, *dinv;
+    const double *x0;      // initial guess or null
+    const double *ax0;     // A*x0 (correct mode with guess) or null
+    double *c_out;         // D^-1 b (kept for ref_compat residual / error bounds); may be null
+    double *t_out, *x_out;
+    uint32_t n;
+    int compat;            // ref_compat: x = (x0 or c) + c ; correct: x = (x0 or 0) + t0
+    LoopCtl *ctl;
+    double *partials;
+    int last_in_iter;
+    int identity_res;
+    int defer_tail;
+    int skip_term0;        // max_terms == 0 / max_iterations == 0: x = base, no term accumulated
+    double *norm_log;
+};
+int32_t launch_init_state(const InitArgs &a, cudaStream_t stream);
+int init_state_grid();
+int32_t launch_scale(double *v, uint64_t n, double factor, cudaStream_t stream);
+// distributed: finish the loop logic after the partial norms were all-reduced (kind: 1 = term, 2 = residual)
+int32_t launch_dist_tail(LoopCtl *ctl, int kind, uint32_t it, int last_in_iter, int identity_res, int force,
+                         double *norm_log, cudaStream_t stream);
+
+}  // namespace sb200

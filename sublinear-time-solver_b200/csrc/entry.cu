@@ -1,0 +1,214 @@
+// entry.cu — batched single-entry estimation (walk-per-thread Monte Carlo) and the PageRank system builder.
+//
+// The Rust crate has no solve_entry; the capability lives in the TS package
+// (SublinearSolver.estimateEntry / performRandomWalk, ref src/core/solver.ts:550-659, 390-432), which builds a
+// dense n x n transition table per call and uses an absorption rule that is only right for special matrices.
+// This implements the unbiased absorbing-walk (Ulam-von Neumann) estimator specified in SURVEY.md Appendix C
+// directly on the CSR rows, keeping the TS defaults: numSamples = max(100, ceil(1/eps^2)) (:587), 1000 steps (:399).
+#include <cmath>
+#include <cstring>
+
+#include "matrix.hpp"
+
+namespace sb200 {
+
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+constexpr int kWalkThreads = 256;
+constexpr int kWalksPerThread = 4;
+
+// grid = (chunks, nqueries). Thread handles walks chunk*1024 + k*256 + tid, k < 4.
+// Walk w of query q draws u_d = (splitmix64(key + d) >> 11) * 2^-53 with
+// key = splitmix64(splitmix64(seed ^ (q+1)*0xA0761D6478BD642F) + w): counter based, so the estimate does not
+// depend on the launch geometry or the GPU count.
+__global__ void __launch_bounds__(kWalkThreads) walk_kernel(const double *__restrict__ vals, const uint32_t *__restrict__ cols,
+                                                            const uint32_t *__restrict__ row_ptr,
+                                                            const double *__restrict__ dinv, const double *__restrict__ b,
+                                                            const uint64_t *__restrict__ qrows, uint64_t nwalks,
+                                                            uint32_t max_steps, uint64_t seed, double *__restrict__ part) {
+    __shared__ double s_a[kWalkThreads / 32], s_b[kWalkThreads / 32];
+    const uint32_t q = blockIdx.y, chunk = blockIdx.x;
+    const uint64_t qkey = splitmix64(seed ^ ((uint64_t)(q + 1) * 0xA0761D6478BD642Full));
+    const uint32_t start = (uint32_t)qrows[q];
+    double sum = 0.0, sumsq = 0.0;
+    for (int k = 0; k < kWalksPerThread; k++) {
+        const uint64_t w = (uint64_t)chunk * (kWalkThreads * kWalksPerThread) + (uint64_t)k * kWalkThreads + threadIdx.x;
+        if (w >= nwalks) break;
+        const uint64_t key = splitmix64(qkey + w);
+        uint32_t s = start;
+        double W = 1.0, acc = 0.0;
+        for (uint32_t step = 0; step < max_steps; step++) {
+            const double ds = dinv[s];
+            acc += W * (b[s] * ds);  // every visited state pays W * c_s, c = D^-1 b
+            const double u = (double)(splitmix64(key + step) >> 11) * (1.0 / 9007199254740992.0);
+            double cum = 0.0;
+            bool moved = false;
+            const uint32_t re = row_ptr[s + 1];
+            for (uint32_t p = row_ptr[s]; p < re; p++) {
+                const uint32_t j = cols[p];
+                if (j == s) continue;
+                const double mv = -(vals[p] * ds);  // M_sj = -a_sj / a_ss
+                cum += fabs(mv);
+                if (cum > u) {  // move with probability |M_sj|, carry its sign
+                    if (mv < 0.0) W = -W;
+                    s = j;
+                    moved = true;
+                    break;
+                }
+            }
+            if (!moved) break;  // absorbed with probability 1 - sum_j |M_sj|
+        }
+        sum += acc;
+        sumsq += acc * acc;
+    }
+    // CTA partial (fixed tree) -> part[q][chunk]; a second kernel adds the chunks in order
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        sumsq += __shfl_xor_sync(0xffffffffu, sumsq, o);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_a[warp] = sum; s_b[warp] = sumsq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, c = 0.0;
+        for (int i = 0; i < kWalkThreads / 32; i++) { a += s_a[i]; c += s_b[i]; }
+        part[((size_t)q * gridDim.x + chunk) * 2 + 0] = a;
+        part[((size_t)q * gridDim.x + chunk) * 2 + 1] = c;
+    }
+}
+
+__global__ void walk_finalize_kernel(const double *__restrict__ part, uint32_t nq, uint32_t chunks, uint64_t nwalks,
+                                     double *__restrict__ est, double *__restrict__ var) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    double a = 0.0, c = 0.0;
+    for (uint32_t k = 0; k < chunks; k++) {
+        a += part[((size_t)q * chunks + k) * 2 + 0];
+        c += part[((size_t)q * chunks + k) * 2 + 1];
+    }
+    const double mean = a / (double)nwalks;
+    est[q] = mean;
+    var[q] = nwalks > 1 ? (c - (double)nwalks * mean * mean) / (double)(nwalks - 1) : 0.0;
+}
+
+int32_t triplets_to_csr(const uint64_t *rows, const uint64_t *cols, const double *vals, uint64_t nt, uint64_t nrows,
+                        uint64_t ncols, int dup_policy, std::vector<uint64_t> &row_ptr, std::vector<uint32_t> &ci,
+                        std::vector<double> &cv);
+
+}  // namespace sb200
+
+using namespace sb200;
+
+extern "C" {
+
+int32_t sb200_solve_entry(const sb200_matrix *m, const double *b, uint64_t blen, const uint64_t *rows,
+                          uint64_t nqueries, double eps, uint64_t nwalks, uint64_t max_steps, uint64_t seed,
+                          double *est, double *var) {
+    clear_error();
+    if (!m) return fail(SB200_ERR_INVALID_INPUT, "null matrix");
+    if (m->distributed) return fail(SB200_ERR_INVALID_INPUT, "solve_entry needs the whole matrix on one GPU (replicate it)");
+    if (m->nrows != m->ncols) return fail(SB200_ERR_INVALID_INPUT, "matrix must be square");
+    if (blen != m->nrows)  // estimateEntry: INVALID_DIMENSIONS (src/core/solver.ts:575-581)
+        return fail(SB200_ERR_DIMENSION_MISMATCH, "Vector length %llu does not match matrix rows %llu",
+                    (unsigned long long)blen, (unsigned long long)m->nrows);
+    if (nqueries && (!rows || !est)) return fail(SB200_ERR_INVALID_INPUT, "null query or output array");
+    if (nwalks == 0) {
+        if (!(eps > 0.0)) return fail(SB200_ERR_INVALID_INPUT, "epsilon must be positive");  // validatePositiveNumber (:583)
+        nwalks = (uint64_t)std::fmax(100.0, std::ceil(1.0 / (eps * eps)));  // :587
+    }
+    if (max_steps == 0) max_steps = 1000;  // :399
+    for (uint64_t q = 0; q < nqueries; q++)
+        if (rows[q] >= m->nrows)  // INVALID_PARAMETERS (:560-566)
+            return fail(SB200_ERR_INDEX_OUT_OF_BOUNDS, "Row index %llu out of bounds. Matrix has %llu rows",
+                        (unsigned long long)rows[q], (unsigned long long)m->nrows);
+    if (nqueries == 0) return SB200_OK;
+    DeviceGuard g(m->device);
+    sb200_matrix *mm = const_cast<sb200_matrix *>(m);
+    SB_TRY(matrix_analyse(mm, SB200_MODE_CORRECT, false));
+    if (m->first_bad_diag[0] != kNone)  // "Zero diagonal at position i" (:369-372)
+        return fail(SB200_ERR_INVALID_SPARSE_MATRIX, "Zero or missing diagonal at position %llu",
+                    (unsigned long long)m->first_bad_diag[0]);
+    if (m->first_bad_dd != kNone)
+        return fail(SB200_ERR_MATRIX_NOT_DIAGONALLY_DOMINANT,
+                    "the absorbing-walk estimator needs row dominance (first violating row %llu)",
+                    (unsigned long long)m->first_bad_dd);
+    const uint64_t per_block = (uint64_t)kWalkThreads * kWalksPerThread;
+    const uint64_t chunks = (nwalks + per_block - 1) / per_block;
+    if (chunks > 0x7FFFFFFFull || nqueries > 65535)
+        return fail(SB200_ERR_INVALID_INPUT, "at most 65535 queries per call and 2^41 walks per query");
+    cudaStream_t st = m->stream;
+    DevBuf<double> d_b, d_part, d_est, d_var;
+    DevBuf<uint64_t> d_q;
+    SB_TRY(d_b.alloc(blen));
+    SB_TRY(d_part.alloc(nqueries * chunks * 2));
+    SB_TRY(d_est.alloc(nqueries));
+    SB_TRY(d_var.alloc(nqueries));
+    SB_TRY(d_q.alloc(nqueries));
+    SB_TRY(copy_h2d(d_b.p, b, blen * 8, st));
+    SB_TRY(copy_h2d(d_q.p, rows, nqueries * 8, st));
+    dim3 grid((unsigned)chunks, (unsigned)nqueries);
+    walk_kernel<<<grid, kWalkThreads, 0, st>>>(m->d_vals.p, m->d_cols.p, m->d_row_ptr.p, m->d_dinv[0].p, d_b.p, d_q.p,
+                                               nwalks, (uint32_t)std::min<uint64_t>(max_steps, 0xFFFFFFFFull), seed,
+                                               d_part.p);
+    SB_CUDA(cudaGetLastError());
+    walk_finalize_kernel<<<(unsigned)((nqueries + 127) / 128), 128, 0, st>>>(d_part.p, (uint32_t)nqueries, (uint32_t)chunks,
+                                                                            nwalks, d_est.p, d_var.p);
+    SB_CUDA(cudaGetLastError());
+    SB_TRY(copy_d2h(est, d_est.p, nqueries * 8, st));
+    if (var) SB_TRY(copy_d2h(var, d_var.p, nqueries * 8, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    return SB200_OK;
+}
+
+// computePageRank (ref src/core/solver.ts:664-722): outdeg[i] = sum_j adj[i][j] (:679-684); S = I, then
+// S[i][j] -= alpha * adj[j][i] / outdeg[j] where outdeg[j] > 0 (:689-698) — dangling rows contribute nothing;
+// rhs = (1 - alpha)/n (:708).  adj is dense in the reference (one number per pair), so repeated edges and a
+// self loop's contribution to the diagonal are merged by summation (SB200_DUP_SUM).
+int32_t sb200_pagerank_system(const uint64_t *src, const uint64_t *dst, const double *w, uint64_t nedges, uint64_t n,
+                              double alpha, sb200_matrix **S, double *rhs) {
+    clear_error();
+    if (!S) return fail(SB200_ERR_INVALID_INPUT, "S is null");
+    *S = nullptr;
+    if (!(alpha >= 0.0 && alpha <= 1.0)) return fail(SB200_ERR_INVALID_INPUT, "damping must be in [0, 1]");  // validateRange (:666)
+    if (nedges && (!src || !dst)) return fail(SB200_ERR_INVALID_INPUT, "null edge list");
+    std::vector<double> outdeg(n, 0.0);
+    for (uint64_t e = 0; e < nedges; e++) {
+        if (src[e] >= n || dst[e] >= n)
+            return fail(SB200_ERR_INDEX_OUT_OF_BOUNDS, "edge %llu (%llu -> %llu) out of bounds for %llu nodes",
+                        (unsigned long long)e, (unsigned long long)src[e], (unsigned long long)dst[e], (unsigned long long)n);
+        outdeg[src[e]] += w ? w[e] : 1.0;
+    }
+    std::vector<uint64_t> tr, tc;
+    std::vector<double> tv;
+    tr.reserve(n + nedges);
+    tc.reserve(n + nedges);
+    tv.reserve(n + nedges);
+    for (uint64_t i = 0; i < n; i++) {
+        tr.push_back(i);
+        tc.push_back(i);
+        tv.push_back(1.0);
+    }
+    for (uint64_t e = 0; e < nedges; e++) {
+        const uint64_t j = src[e], i = dst[e];
+        if (outdeg[j] > 0.0) {
+            tr.push_back(i);
+            tc.push_back(j);
+            tv.push_back(-(alpha * ((w ? w[e] : 1.0) / outdeg[j])));
+        }
+    }
+    std::vector<uint64_t> rp;
+    std::vector<uint32_t> ci;
+    std::vector<double> cv;
+    SB_TRY(triplets_to_csr(tr.data(), tc.data(), tv.data(), tv.size(), n, n, SB200_DUP_SUM, rp, ci, cv));
+    SB_TRY(matrix_from_host_csr(rp.data(), nullptr, ci.data(), cv.data(), n, n, rp[n], false, S));
+    if (rhs)
+        for (uint64_t i = 0; i < n; i++) rhs[i] = (1.0 - alpha) / (double)n;
+    return SB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,575 @@
+// kernels.cu — the sm_100a kernels of the push-iteration path.
+//
+// One kernel template does every pass over the CSR store; what differs is the per-row epilogue:
+//   EPI_SPMV  : y = A x                      Matrix::multiply_vector        (ref src/matrix/sparse.rs:187-203)
+//   EPI_PUSH  : t' = t - D^-1 (A t); x += t'; ||t'||^2     apply_iteration_matrix + accumulate + l2_norm
+//                                            (ref src/solver/neumann.rs:280-299, 264-266, 271)
+//   EPI_RESID : ||A x - rhs||^2               update_residual               (ref src/solver/neumann.rs:302-318)
+//
+// B200 mapping (HBM-bound sparse gather-reduce; tensor cores are irrelevant here):
+//   * rows are grouped on the host into TILES of <= NT rows and <= CAP non-zeros (CSR-adaptive style);
+//     a persistent grid (multiple of the SM count) walks the tile list.
+//   * the tile's contiguous slices of `values` (f64) and `col_indices` (u32) are streamed HBM -> shared
+//     memory by the TMA engine as 1-D bulk copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP),
+//     double-buffered, with an L2 evict_first policy: the 12 B/nnz stream never occupies LSU/L1 issue slots
+//     and does not push the gather source out of L2.
+//   * all NT threads then gather x[col] (L2 evict_last policy: the 8n-byte term vector is the only data
+//     with reuse) and overwrite the staged value with the product, in place.
+//   * one thread per row sums its products left to right, exactly the reference's accumulation order, with
+//     FMA contraction disabled (-fmad=false) so a row sum is bit-identical to CSRStorage::multiply_vector.
+//   * the epilogue (diagonal scale, term/solution update, squared norm) is fused; norms are reduced
+//     deterministically (fixed-shape tree per CTA, fixed-order sum of CTA partials by the last CTA) and
+//     the last CTA also advances the device-resident loop state (LoopCtl), so the host never has to
+//     synchronise per term.
+//   * a row with more than CAP non-zeros is a tile of its own and is streamed with coalesced loads by the
+//     whole CTA (lane-strided partial sums + tree: order differs from the reference, tolerance-level only).
+#include "common.hpp"
+
+namespace sb200 {
+
+const TileCfg kTileCfgs[kNumTileCfgs] = {{256, 3584}, {128, 1792}, {512, 7168}};
+
+int default_tile_cfg() {
+    static int cfg = [] {
+        const char *e = getenv("SUBLINEAR_B200_TILE_CFG");
+        int v = e ? atoi(e) : 0;
+        return (v >= 0 && v < kNumTileCfgs) ? v : 0;
+    }();
+    return cfg;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D TMA bulk copy + cache policies
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy executed by the TMA unit; completion is signalled on `bar` in bytes.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar,
+                                         uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+// order generic-proxy accesses to shared memory before later async-proxy (TMA) writes to the same bytes
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// the random gather: read-only path, keep the line in L2 (it is the only reused data of the iteration)
+__device__ __forceinline__ double ld_gather(const double *p, uint64_t policy) {
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+    return v;
+}
+// streaming loads for the long-row path
+__device__ __forceinline__ double ld_stream_f64(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// deterministic reductions + device-side loop control
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sum over the CTA; result valid in thread 0. s_red: NT/32 doubles.
+template <int NT>
+__device__ __forceinline__ double block_sum(double v, double *s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // s_red may still be read from a previous call
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (warp == 0) {
+        r = (lane < NT / 32) ? s_red[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// End of one iteration of the `while` loop in NeumannSolver::solve (ref src/solver/neumann.rs:498-512 and the
+// loop condition :481 evaluated for the next iteration).
+__device__ __forceinline__ void end_of_iteration(LoopCtl *c, uint32_t it) {
+    c->iterations = it + 1;
+    if (!isfinite(c->res_norm)) {  // :501-507 NumericalInstability
+        c->nonfinite = 1;
+        c->alive = 0;
+        return;
+    }
+    if (c->sconv) {  // :510-512
+        c->alive = 0;
+        return;
+    }
+    // :481 `!is_converged && iterations < max_iterations`; series_converged is false here, so
+    // is_converged (:422-430) reduces to residual_norm <= tolerance.
+    if (c->res_norm <= c->tolerance || it + 1 >= c->max_iterations) c->alive = 0;
+}
+
+enum TailKind { TAIL_NONE = 0, TAIL_TERM = 1, TAIL_RESID = 2 };
+
+__device__ __forceinline__ void tail_logic(LoopCtl *c, int kind, double sum, double aux, uint32_t it, int last_in_iter,
+                                           int identity_res, int defer, double *norm_log) {
+    if (defer) {  // row-partitioned: publish this rank's sums; dist_tail_kernel finishes after the allreduce
+        c->red[0] = sum;
+        c->red[1] = aux;
+        return;
+    }
+    if (kind == TAIL_TERM) {
+        c->term_norm2 = sum;
+        if (norm_log) norm_log[it] = sum;
+        if (identity_res) c->aux_norm2 = aux;
+        c->terms = it + 1;  // ref :268
+        if (it == 0) c->rhs_norm2 = sum;
+        if (sqrt(sum) < c->series_tolerance) c->sconv = 1;  // ref :271-274
+        if (identity_res) {
+            c->res_norm2 = aux;
+            c->res_norm = sqrt(aux);
+        }
+    } else if (kind == TAIL_RESID) {
+        c->res_norm2 = sum;
+        c->res_norm = sqrt(sum);  // ref :316
+    }
+    if (last_in_iter) end_of_iteration(c, it);
+}
+
+// CTA partial -> global partial array -> the last CTA to arrive sums all partials in index order.
+template <int NT>
+__device__ __forceinline__ void grid_reduce_and_tail(double sq, double aux, LoopCtl *ctl, double *partials, int kind,
+                                                     uint32_t it, int last_in_iter, int identity_res, int defer,
+                                                     double *norm_log, double *s_red, int *s_flag) {
+    double bs = block_sum<NT>(sq, s_red);
+    double ba = identity_res ? block_sum<NT>(aux, s_red) : 0.0;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = bs;
+        if (identity_res) partials[gridDim.x + blockIdx.x] = ba;
+        __threadfence();
+        unsigned t = atomicAdd(&ctl->ticket, 1u);
+        *s_flag = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (*s_flag) {
+        __threadfence();
+        double s = 0.0, a = 0.0;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += NT) s += __ldcg(partials + i);
+        if (identity_res)
+            for (unsigned i = threadIdx.x; i < gridDim.x; i += NT) a += __ldcg(partials + gridDim.x + i);
+        s = block_sum<NT>(s, s_red);
+        if (identity_res) a = block_sum<NT>(a, s_red);
+        if (threadIdx.x == 0) {
+            ctl->ticket = 0;
+            tail_logic(ctl, kind, s, a, it, last_in_iter, identity_res, defer, norm_log);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the tile kernel
+// ---------------------------------------------------------------------------------------------------------
+template <int NT, int CAP>
+struct TileSmem {
+    static constexpr int kElems = CAP + 8;  // shift (<=3) + round-up (<=3) slack
+    static constexpr size_t kStageBytes = (size_t)kElems * 12;
+    static constexpr size_t kBytes = 2 * kStageBytes;
+};
+
+template <int EPI, int NT, int CAP>
+__global__ void __launch_bounds__(NT) tile_kernel(const TileKernelArgs a) {
+    using SM = TileSmem<NT, CAP>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ double s_red[NT / 32];
+    __shared__ int s_flag;
+
+    if (EPI != EPI_SPMV) {
+        if (!a.force && a.ctl->alive == 0) return;  // loop already finished: no-op launch
+    }
+
+    const int tid = threadIdx.x;
+    // stage s: [kElems f64 values | kElems u32 column indices]
+    auto s_val = [&](int s) { return reinterpret_cast<double *>(smem_raw + (size_t)s * SM::kStageBytes); };
+    auto s_col = [&](int s) {
+        return reinterpret_cast<uint32_t *>(smem_raw + (size_t)s * SM::kStageBytes + (size_t)SM::kElems * 8);
+    };
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const uint64_t pol_stream = policy_evict_first();
+    const uint64_t pol_gather = policy_evict_last();
+    const TileDesc *__restrict__ tiles = a.tiles;
+
+    // producer side: one thread programs the TMA unit for a whole tile
+    auto issue = [&](uint32_t tile, int stage) {
+        const TileDesc d0 = tiles[tile], d1 = tiles[tile + 1];
+        const uint32_t cnt = d1.nnz0 - d0.nnz0;
+        if (cnt == 0 || cnt > (uint32_t)CAP) return;  // empty tile / long-row tile: nothing staged
+        const uint32_t a0 = d0.nnz0 & ~3u;
+        const uint32_t nel = ((d0.nnz0 - a0) + cnt + 3u) & ~3u;
+        mbar_arrive_expect_tx(&s_bar[stage], nel * 12u);
+        bulk_g2s(s_val(stage), a.vals + a0, nel * 8u, &s_bar[stage], pol_stream);
+        bulk_g2s(s_col(stage), a.cols + a0, nel * 4u, &s_bar[stage], pol_stream);
+    };
+
+    uint32_t tile = blockIdx.x;
+    uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
+    if (tid == 0 && tile < a.ntiles) issue(tile, 0);
+
+    double sq = 0.0, aux = 0.0;
+    int stage = 0;
+    for (; tile < a.ntiles; tile += gridDim.x, stage ^= 1) {
+        const uint32_t next = tile + gridDim.x;
+        if (tid == 0 && next < a.ntiles) issue(next, stage ^ 1);
+
+        const TileDesc d0 = tiles[tile], d1 = tiles[tile + 1];
+        const uint32_t row0 = d0.row0, nrows = d1.row0 - d0.row0;
+        const uint32_t nnz0 = d0.nnz0, cnt = d1.nnz0 - d0.nnz0;
+        const bool is_long = cnt > (uint32_t)CAP;  // exactly one row, streamed by the whole CTA
+        const uint32_t a0 = nnz0 & ~3u;
+        const uint32_t shift = nnz0 - a0;
+
+        // per-row operands of the epilogue: issue these loads before waiting on the tile
+        const bool active = (uint32_t)tid < nrows;
+        const uint32_t row = row0 + tid;
+        uint32_t rs = 0, re = 0;
+        double own = 0.0, dv = 0.0, xs = 0.0, rh = 0.0;
+        if (active) {
+            rs = a.row_ptr[row];
+            re = a.row_ptr[row + 1];
+            if (EPI == EPI_PUSH) {
+                own = a.xin_own[row];
+                dv = a.dinv[row];
+                xs = a.sol[row];
+            } else if (EPI == EPI_RESID) {
+                rh = a.rhs[row];
+            } else if (a.accumulate) {
+                xs = a.out[row];
+            }
+        }
+
+        double sum = 0.0;
+        if (!is_long) {
+            if (cnt > 0) {
+                mbar_wait(&s_bar[stage], (phase_bits >> stage) & 1u);
+                phase_bits ^= (1u << stage);
+                double *__restrict__ sv = s_val(stage) + shift;
+                const uint32_t *__restrict__ sc = s_col(stage) + shift;
+                // gather phase: 4 independent gathers in flight per thread
+                for (uint32_t base = 0; base < cnt; base += 4u * NT) {
+                    uint32_t j[4];
+                    double xv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) j[u] = base + u * NT + tid;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) xv[u] = (j[u] < cnt) ? ld_gather(a.xin + sc[j[u]], pol_gather) : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (j[u] < cnt) sv[j[u]] = sv[j[u]] * xv[u];
+                }
+            }
+            __syncthreads();
+            if (active) {
+                // left-to-right accumulation, the order of CSRStorage::multiply_vector_add (sparse.rs:193-203)
+                const double *__restrict__ sp = s_val(stage) - a0;
+                double acc = (EPI == EPI_SPMV && a.accumulate) ? xs : 0.0;
+                for (uint32_t k = rs; k < re; k++) acc += sp[k];
+                sum = acc;
+            }
+        } else {
+            double acc = 0.0;
+            for (uint32_t k = nnz0 + tid; k < nnz0 + cnt; k += NT)
+                acc += ld_stream_f64(a.vals + k) * ld_gather(a.xin + ld_stream_u32(a.cols + k), pol_gather);
+            acc = block_sum<NT>(acc, s_red);
+            if (tid == 0) sum = (EPI == EPI_SPMV && a.accumulate) ? xs + acc : acc;
+        }
+
+        if (active) {
+            if (EPI == EPI_SPMV) {
+                a.out[row] = sum;
+            } else if (EPI == EPI_PUSH) {
+                const double tmp = sum * dv;  // temp *= d_inv        (neumann.rs:289-291)
+                const double tn = own - tmp;  // term -= temp         (neumann.rs:294-296)
+                a.out[row] = tn;
+                a.sol[row] = xs + tn;         // solution += term     (neumann.rs:264-266)
+                sq += tn * tn;                // l2_norm accumulation (solver/mod.rs:369-371)
+                if (a.identity_res) {
+                    const double r = tn / dv;  // (D o t')_i = (b - A x)_i, SURVEY F12
+                    aux += r * r;
+                }
+            } else {
+                const double r = sum - rh;    // r = A x - rhs        (neumann.rs:308-310)
+                sq += r * r;
+            }
+        }
+        // every thread is done with this stage's buffers before the TMA refills them (issued next iteration)
+        fence_proxy_async_smem();
+        __syncthreads();
+    }
+
+    if (EPI != EPI_SPMV) {
+        grid_reduce_and_tail<NT>(sq, aux, a.ctl, a.partials, EPI == EPI_PUSH ? TAIL_TERM : TAIL_RESID, a.it,
+                                 a.last_in_iter, a.identity_res, a.defer_tail, a.norm_log, s_red, &s_flag);
+    }
+}
+
+template <int EPI, int NT, int CAP>
+static int32_t launch_one(const TileKernelArgs &a, cudaStream_t stream, int *max_grid_out) {
+    using SM = TileSmem<NT, CAP>;
+    static int max_grid[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) return fail(SB200_ERR_ALGORITHM, "device index %d out of range", dev);
+    if (max_grid[dev] == 0) {
+        SB_CUDA(cudaFuncSetAttribute(tile_kernel<EPI, NT, CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)SM::kBytes));
+        int per_sm = 0, sms = 0;
+        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_kernel<EPI, NT, CAP>, NT, SM::kBytes));
+        SB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (per_sm < 1) return fail(SB200_ERR_ALGORITHM, "tile kernel does not fit on an SM");
+        max_grid[dev] = per_sm * sms;  // persistent grid: a whole number of CTAs per SM (148 SMs on B200)
+    }
+    if (max_grid_out) {
+        *max_grid_out = max_grid[dev];
+        return SB200_OK;
+    }
+    if (a.ntiles == 0 && EPI == EPI_SPMV) return SB200_OK;
+    unsigned grid = a.ntiles < (uint32_t)max_grid[dev] ? a.ntiles : (uint32_t)max_grid[dev];
+    if (grid == 0) grid = 1;  // reductions still need their tail
+    tile_kernel<EPI, NT, CAP><<<grid, NT, SM::kBytes, stream>>>(a);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+template <int NT, int CAP>
+static int32_t launch_cfg(Epilogue epi, const TileKernelArgs &a, cudaStream_t stream, int *mg) {
+    switch (epi) {
+        case EPI_SPMV: return launch_one<EPI_SPMV, NT, CAP>(a, stream, mg);
+        case EPI_PUSH: return launch_one<EPI_PUSH, NT, CAP>(a, stream, mg);
+        default: return launch_one<EPI_RESID, NT, CAP>(a, stream, mg);
+    }
+}
+
+static int32_t launch_any(int cfg, Epilogue epi, const TileKernelArgs &a, cudaStream_t stream, int *mg) {
+    switch (cfg) {
+        case 0: return launch_cfg<256, 3584>(epi, a, stream, mg);
+        case 1: return launch_cfg<128, 1792>(epi, a, stream, mg);
+        case 2: return launch_cfg<512, 7168>(epi, a, stream, mg);
+        default: return fail(SB200_ERR_INVALID_INPUT, "unknown tile configuration %d", cfg);
+    }
+}
+
+int32_t launch_tile_kernel(int cfg, Epilogue epi, const TileKernelArgs &a, cudaStream_t stream) {
+    return launch_any(cfg, epi, a, stream, nullptr);
+}
+
+int tile_kernel_max_grid(int cfg, Epilogue epi) {
+    int mg = 0;
+    TileKernelArgs dummy{};
+    if (launch_any(cfg, epi, dummy, nullptr, &mg) != SB200_OK) return 0;
+    return mg;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4: setup pass — dominance, diagonal, D^-1   (ref src/solver/neumann.rs:162-188, src/matrix/mod.rs:467-485)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_u64(unsigned long long *addr, unsigned long long v) { atomicMin(addr, v); }
+
+__global__ void setup_rows_kernel(const double *__restrict__ vals, const uint32_t *__restrict__ cols,
+                                  const uint32_t *__restrict__ row_ptr, uint32_t nrows, int compat_diag, SetupOut o) {
+    for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += gridDim.x * blockDim.x) {
+        const uint32_t rs = row_ptr[row], re = row_ptr[row + 1];
+        double diag_last = 0.0, diag_sum = 0.0, off = 0.0;
+        bool has = false;
+        for (uint32_t k = rs; k < re; k++) {
+            const uint32_t c = cols[k];
+            const double v = vals[k];
+            if (c == row) {
+                diag_last = fabs(v);  // `diagonal = value.abs()` is overwritten per entry (mod.rs:474-476)
+                diag_sum += v;
+                has = true;
+            } else {
+                off += fabs(v);
+                if (o.col_off) atomicAdd(o.col_off + c, fabs(v));
+            }
+        }
+        if (o.col_diag && has) o.col_diag[row] = diag_last;
+        if (diag_last < off) atomic_min_u64(o.first_bad_dd, row);  // mod.rs:480
+        double d = diag_sum;
+        if (compat_diag && has) {
+            // CSRStorage::get (sparse.rs:142-155): bisection over the (column-sorted) row; with duplicated
+            // diagonal entries it returns whichever one the probe sequence meets first.
+            uint32_t lo = rs, hi = re;
+            bool found = false;
+            while (lo < hi) {
+                const uint32_t mid = lo + (hi - lo) / 2;
+                const uint32_t c = cols[mid];
+                if (c == row) {
+                    d = vals[mid];
+                    found = true;
+                    break;
+                }
+                if (c < row) lo = mid + 1; else hi = mid;
+            }
+            if (!found) has = false;  // unsorted row: the reference's binary search would miss it too
+        }
+        if (!has || fabs(d) < 1e-14) {  // neumann.rs:174-187
+            atomic_min_u64(o.first_bad_diag, row);
+            o.dinv[row] = 0.0;
+        } else {
+            o.dinv[row] = 1.0 / d;
+        }
+        if (o.min_factor_bits && off > 0.0) {
+            // positive doubles order like their bit patterns
+            atomicMin(reinterpret_cast<unsigned long long *>(o.min_factor_bits),
+                      (unsigned long long)__double_as_longlong(diag_last / off));
+        }
+    }
+}
+
+int32_t launch_setup_rows(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
+                          int compat_diag, SetupOut out, cudaStream_t stream) {
+    if (nrows == 0) return SB200_OK;
+    unsigned grid = (nrows + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    setup_rows_kernel<<<grid, 256, 0, stream>>>(vals, cols, row_ptr, nrows, compat_diag, out);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+__global__ void col_dominance_kernel(const double *__restrict__ col_diag, const double *__restrict__ col_off, uint32_t n,
+                                     unsigned long long *first_bad) {
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x)
+        if (col_diag[c] < col_off[c]) atomic_min_u64(first_bad, c);
+}
+
+int32_t launch_col_dominance(const double *col_diag, const double *col_off, uint32_t n, unsigned long long *first_bad,
+                             cudaStream_t stream) {
+    if (n == 0) return SB200_OK;
+    unsigned grid = (n + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    col_dominance_kernel<<<grid, 256, 0, stream>>>(col_diag, col_off, n, first_bad);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// iteration 0: scaled rhs, first term, first accumulation (ref neumann.rs:191-211 and compute_next_term k=0)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kInitThreads = 256;
+
+__global__ void __launch_bounds__(kInitThreads) init_state_kernel(const InitArgs a) {
+    __shared__ double s_red[kInitThreads / 32];
+    __shared__ int s_flag;
+    double sq = 0.0, aux = 0.0;
+    for (uint32_t i = blockIdx.x * kInitThreads + threadIdx.x; i < a.n; i += gridDim.x * kInitThreads) {
+        const double dv = a.dinv[i];
+        const double bi = a.b[i];
+        const double c = bi * dv;  // rhs = b o D^-1 (neumann.rs:191-194)
+        if (a.c_out) a.c_out[i] = c;
+        double t0, base;
+        if (a.compat) {
+            t0 = c;                          // current_term = rhs.clone()      (neumann.rs:211)
+            base = a.x0 ? a.x0[i] : c;       // solution = initial_guess or rhs (neumann.rs:197-208)
+        } else {
+            t0 = a.ax0 ? (bi - a.ax0[i]) * dv : c;  // t0 = D^-1 (b - A x0)
+            base = a.x0 ? a.x0[i] : 0.0;
+        }
+        a.t_out[i] = t0;
+        a.x_out[i] = a.skip_term0 ? base : base + t0;  // k = 0: solution += term (neumann.rs:264-266)
+        sq += t0 * t0;
+        if (a.identity_res) {
+            const double r = t0 / dv;
+            aux += r * r;
+        }
+    }
+    grid_reduce_and_tail<kInitThreads>(sq, aux, a.ctl, a.partials, TAIL_TERM, 0u, a.last_in_iter, a.identity_res,
+                                       a.defer_tail, a.norm_log, s_red, &s_flag);
+}
+
+int init_state_grid() { return 148 * 4; }
+
+int32_t launch_init_state(const InitArgs &a, cudaStream_t stream) {
+    unsigned grid = (a.n + kInitThreads - 1) / kInitThreads;
+    if (grid > (unsigned)init_state_grid()) grid = init_state_grid();
+    if (grid == 0) grid = 1;
+    init_state_kernel<<<grid, kInitThreads, 0, stream>>>(a);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+__global__ void scale_kernel(double *v, uint64_t n, double f) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        v[i] *= f;
+}
+
+// Row-partitioned runs: the tile kernel only published this rank's partial sums (defer_tail); after the
+// allreduce every rank holds the global sums and takes the same decision here.
+__global__ void dist_tail_kernel(LoopCtl *c, int kind, uint32_t it, int last_in_iter, int identity_res, int force,
+                                 double *norm_log) {
+    if (c->alive == 0 && !force) return;  // dead loop: red[] only holds re-reduced garbage
+    tail_logic(c, kind, c->red[0], c->red[1], it, last_in_iter, identity_res, 0, norm_log);
+}
+
+int32_t launch_dist_tail(LoopCtl *ctl, int kind, uint32_t it, int last_in_iter, int identity_res, int force,
+                         double *norm_log, cudaStream_t stream) {
+    dist_tail_kernel<<<1, 1, 0, stream>>>(ctl, kind, it, last_in_iter, identity_res, force, norm_log);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+int32_t launch_scale(double *v, uint64_t n, double factor, cudaStream_t stream) {
+    if (n == 0) return SB200_OK;
+    uint64_t g = (n + 255) / 256;
+    unsigned grid = g > 148ull * 16 ? 148u * 16 : (unsigned)g;
+    scale_kernel<<<grid, 256, 0, stream>>>(v, n, factor);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+}  // namespace sb200

@@ -1,0 +1,89 @@
+// matrix.hpp — the device-resident SparseMatrix handle (internal).
+#pragma once
+
+#include <memory>
+
+#include "common.hpp"
+
+namespace sb200 {
+
+constexpr unsigned long long kNone = ~0ull;
+
+// Per-solve device vectors + pinned control mirror; pooled on the matrix so that concurrent solves on one
+// handle each get their own (the reference's solve(&self, ..) is re-entrant: all mutable state is per call).
+struct Workspace {
+    uint64_t n_local = 0, n_full = 0;
+    DevBuf<double> t[2];      // term ping-pong (full length n_full when distributed)
+    DevBuf<double> x;         // solution (local rows)
+    DevBuf<double> c;         // D^-1 b
+    DevBuf<double> b;         // staged right-hand side (host API)
+    DevBuf<double> tmp;       // A*x0 / initial guess staging
+    DevBuf<double> partials;  // CTA partial sums
+    DevBuf<double> norm_log;  // per-term norms (bare recurrence)
+    DevBuf<LoopCtl> ctl;
+    LoopCtl *h_ctl = nullptr;  // pinned
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ~Workspace();
+    int32_t ensure(uint64_t n_local, uint64_t n_full, size_t npartials);
+    uint64_t bytes() const;
+};
+
+}  // namespace sb200
+
+struct sb200_matrix {
+    int device = 0;
+    uint64_t nrows = 0, ncols = 0, nnz = 0;
+    int tile_cfg = 0;
+    uint32_t ntiles = 0;
+    std::vector<uint32_t> h_row_ptr;  // host copy, nrows + 1
+    sb200::DevBuf<double> d_vals;
+    sb200::DevBuf<uint32_t> d_cols;
+    sb200::DevBuf<uint32_t> d_row_ptr;
+    sb200::DevBuf<sb200::TileDesc> d_tiles;
+    cudaStream_t stream = nullptr;  // for host-pointer entry points
+
+    // distributed: this handle holds rows [row_base, row_base + nrows) of an n_global-square system
+    uint64_t row_base = 0;
+    uint64_t n_global = 0;
+    bool distributed = false;
+
+    // lazily computed analysis (K4), cached: the matrix is immutable apart from scale()
+    std::mutex mu;
+    bool analysed[2] = {false, false};  // per solve mode (diagonal extraction differs on duplicates)
+    bool col_analysed = false;
+    sb200::DevBuf<double> d_dinv[2];
+    unsigned long long first_bad_dd = sb200::kNone, first_bad_diag[2] = {sb200::kNone, sb200::kNone};
+    unsigned long long first_bad_col = sb200::kNone;
+    double min_factor = 0.0;
+    bool has_factor = false;
+
+    std::vector<std::unique_ptr<sb200::Workspace>> pool;
+
+    ~sb200_matrix();
+};
+
+namespace sb200 {
+
+// ingest helpers (matrix.cu)
+int32_t matrix_from_host_csr(const uint64_t *row_ptr64, const uint32_t *row_ptr32, const uint32_t *cols,
+                             const double *vals, uint64_t nrows, uint64_t ncols, uint64_t nnz, bool validate,
+                             sb200_matrix **out);
+int32_t matrix_analyse(sb200_matrix *m, int mode, bool need_cols);
+int32_t matrix_spmv_dev(const sb200_matrix *m, const double *x_dev, double *y_dev, int accumulate, cudaStream_t st);
+std::unique_ptr<Workspace> matrix_acquire_ws(sb200_matrix *m);
+void matrix_release_ws(sb200_matrix *m, std::unique_ptr<Workspace> ws);
+void fill_tile_args(const sb200_matrix *m, TileKernelArgs &a);
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace sb200

@@ -1,0 +1,191 @@
+// runtime.cu — error reporting, device selection, pinned host memory and host<->device copies.
+#include <cstdlib>
+#include <cstring>
+
+#include "common.hpp"
+
+namespace sb200 {
+
+static thread_local std::string t_last_error;
+static thread_local int t_device = -1;
+
+int32_t fail(int32_t code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    t_last_error = buf;
+    if (const char *e = getenv("SUBLINEAR_B200_LOG"))
+        if (e[0] == '1') fprintf(stderr, "[sublinear_b200] error %d: %s\n", code, buf);
+    return code;
+}
+
+void clear_error() { t_last_error.clear(); }
+
+int current_device() {
+    if (t_device < 0) {
+        const char *e = getenv("SUBLINEAR_B200_DEVICE");
+        t_device = e ? atoi(e) : 0;
+    }
+    return t_device;
+}
+
+// The product path has no CPU fallback: a missing/unusable GPU is an error, loudly.
+int32_t require_device(int dev) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(SB200_ERR_ALGORITHM,
+                    "no usable CUDA device (%s); sublinear_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (dev < 0 || dev >= count) return fail(SB200_ERR_INVALID_INPUT, "device %d out of range (0..%d)", dev, count - 1);
+    SB_CUDA(cudaSetDevice(dev));
+    return SB200_OK;
+}
+
+// ---- staged copies -----------------------------------------------------------------------------------
+static bool is_pinned_or_device(const void *p) {
+    cudaPointerAttributes at;
+    cudaError_t e = cudaPointerGetAttributes(&at, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+namespace {
+struct StagingRing {
+    static constexpr size_t kChunk = 8u << 20;
+    void *buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::mutex mu;
+    int32_t ensure() {
+        for (int i = 0; i < 2; i++) {
+            if (!buf[i]) SB_CUDA(cudaHostAlloc(&buf[i], kChunk, cudaHostAllocDefault));
+            if (!ev[i]) SB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+        }
+        return SB200_OK;
+    }
+};
+StagingRing g_ring;
+}  // namespace
+
+int32_t copy_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream) {
+    if (bytes == 0) return SB200_OK;
+    if (is_pinned_or_device(src_host)) {
+        SB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyDefault, stream));
+        return SB200_OK;
+    }
+    std::lock_guard<std::mutex> lk(g_ring.mu);
+    SB_TRY(g_ring.ensure());
+    size_t off = 0;
+    for (int i = 0; off < bytes; i ^= 1) {
+        size_t n = bytes - off < StagingRing::kChunk ? bytes - off : StagingRing::kChunk;
+        SB_CUDA(cudaEventSynchronize(g_ring.ev[i]));  // previous DMA out of this slot finished
+        memcpy(g_ring.buf[i], (const char *)src_host + off, n);
+        SB_CUDA(cudaMemcpyAsync((char *)dst_dev + off, g_ring.buf[i], n, cudaMemcpyHostToDevice, stream));
+        SB_CUDA(cudaEventRecord(g_ring.ev[i], stream));
+        off += n;
+    }
+    SB_CUDA(cudaEventSynchronize(g_ring.ev[0]));
+    SB_CUDA(cudaEventSynchronize(g_ring.ev[1]));
+    return SB200_OK;
+}
+
+int32_t copy_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t stream) {
+    if (bytes == 0) return SB200_OK;
+    if (is_pinned_or_device(dst_host)) {
+        SB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDefault, stream));
+        SB_CUDA(cudaStreamSynchronize(stream));
+        return SB200_OK;
+    }
+    std::lock_guard<std::mutex> lk(g_ring.mu);
+    SB_TRY(g_ring.ensure());
+    size_t off = 0, prev_off = 0, prev_n = 0;
+    int prev = -1;
+    for (int i = 0; off < bytes; i ^= 1) {
+        size_t n = bytes - off < StagingRing::kChunk ? bytes - off : StagingRing::kChunk;
+        SB_CUDA(cudaMemcpyAsync(g_ring.buf[i], (const char *)src_dev + off, n, cudaMemcpyDeviceToHost, stream));
+        SB_CUDA(cudaEventRecord(g_ring.ev[i], stream));
+        if (prev >= 0) {
+            SB_CUDA(cudaEventSynchronize(g_ring.ev[prev]));
+            memcpy((char *)dst_host + prev_off, g_ring.buf[prev], prev_n);
+        }
+        prev = i;
+        prev_off = off;
+        prev_n = n;
+        off += n;
+    }
+    if (prev >= 0) {
+        SB_CUDA(cudaEventSynchronize(g_ring.ev[prev]));
+        memcpy((char *)dst_host + prev_off, g_ring.buf[prev], prev_n);
+    }
+    return SB200_OK;
+}
+
+}  // namespace sb200
+
+using namespace sb200;
+
+extern "C" {
+
+int32_t sb200_abi_version(void) { return SB200_ABI_VERSION; }
+
+size_t sb200_last_error(char *buf, size_t cap) {
+    size_t n = t_last_error.size();
+    if (buf && cap > 0) {
+        size_t k = n < cap - 1 ? n : cap - 1;
+        memcpy(buf, t_last_error.data(), k);
+        buf[k] = 0;
+    }
+    return n;
+}
+
+int32_t sb200_device_count(int32_t *count) {
+    if (!count) return fail(SB200_ERR_INVALID_INPUT, "count is null");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        c = 0;
+    }
+    *count = c;
+    return SB200_OK;
+}
+
+int32_t sb200_set_device(int32_t device) {
+    SB_TRY(require_device(device));
+    t_device = device;
+    return SB200_OK;
+}
+
+int32_t sb200_get_device(int32_t *device) {
+    if (!device) return fail(SB200_ERR_INVALID_INPUT, "device is null");
+    *device = current_device();
+    return SB200_OK;
+}
+
+int32_t sb200_host_alloc(uint64_t bytes, void **out) {
+    if (!out) return fail(SB200_ERR_INVALID_INPUT, "out is null");
+    *out = nullptr;
+    SB_TRY(require_device(current_device()));
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SB200_ERR_MEMORY_ALLOCATION, "cudaHostAlloc of %llu bytes failed: %s", (unsigned long long)bytes,
+                    cudaGetErrorString(e));
+    }
+    return SB200_OK;
+}
+
+int32_t sb200_host_free(void *ptr) {
+    if (!ptr) return SB200_OK;
+    SB_CUDA(cudaFreeHost(ptr));
+    return SB200_OK;
+}
+
+}  // extern "C"

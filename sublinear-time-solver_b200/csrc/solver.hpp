@@ -1,0 +1,26 @@
+// solver.hpp — NeumannSolver handle and the device-side solve core (internal).
+#pragma once
+
+#include "matrix.hpp"
+
+struct sb200_solver {
+    uint64_t max_terms = 50;          // NeumannSolver.max_terms          (ref src/solver/neumann.rs:26)
+    double series_tolerance = 1e-8;   // NeumannSolver.series_tolerance   (:28)
+    int adaptive_truncation = 1;      // (:30)
+    int cache_powers = 1;             // (:32) carried, unused: the reference never fills matrix_powers
+};
+
+namespace sb200 {
+
+struct SolveStats {
+    uint64_t iterations = 0, terms = 0, matvec = 0, launches = 0;
+    bool converged = false, series_converged = false, nonfinite = false;
+    double residual_norm = 0, last_term_norm = 0, rhs_norm = 0;
+    float device_ms = 0;
+};
+
+int32_t validate_options(const sb200_options *opt);
+int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev, const double *x0_dev,
+                     const sb200_options *opt, double *x_out_dev, cudaStream_t st, Workspace &ws, SolveStats &stats);
+
+}  // namespace sb200

@@ -1,0 +1,573 @@
+"""ctypes binding of libsublinear_b200.so — the Python-side mirror of the reference crate's API for the
+Neumann / push-iteration path (names follow the Rust crate: SparseMatrix, NeumannSolver, SolverOptions,
+SolverResult, SolverError).  Used by tests/ and bench.py; it adds no compute of its own: every call goes
+through the C ABI declared in include/sublinear_b200.h, and there is no CPU fallback — a missing library or
+GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(PKG_DIR, "libsublinear_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(PKG_DIR), "include", "sublinear_b200.h")
+
+OK = 0
+ERROR_NAMES = {
+    1: "MatrixNotDiagonallyDominant", 2: "NumericalInstability", 3: "ConvergenceFailure", 4: "InvalidInput",
+    5: "DimensionMismatch", 6: "UnsupportedMatrixFormat", 7: "MemoryAllocationError", 8: "IndexOutOfBounds",
+    9: "InvalidSparseMatrix", 10: "AlgorithmError", 11: "WasmBindingError", 12: "IoError", 13: "SerializationError",
+}
+MODE_CORRECT, MODE_REF_COMPAT = 0, 1
+DOMINANCE_ROW, DOMINANCE_ROW_OR_COL = 0, 1
+RESIDUAL_EVERY_5, RESIDUAL_IDENTITY = 0, 1
+DUP_KEEP, DUP_SUM = 0, 1
+UNIQUE_ID_BYTES = 128
+
+
+class SolverError(Exception):
+    """`enum SolverError` (src/error.rs:16-138): .code is the 1-based variant index, .variant its name."""
+
+    def __init__(self, code: int, message: str, result=None):
+        super().__init__(f"{ERROR_NAMES.get(code, code)}: {message}")
+        self.code = code
+        self.variant = ERROR_NAMES.get(code, str(code))
+        self.message = message
+        self.result = result  # iterations / residual_norm of ConvergenceFailure / NumericalInstability
+
+
+class _Options(C.Structure):
+    _fields_ = [("tolerance", C.c_double), ("max_iterations", C.c_uint64), ("convergence_mode", C.c_int32),
+                ("norm_type", C.c_int32), ("collect_stats", C.c_int32), ("streaming_interval", C.c_uint64),
+                ("initial_guess", C.c_void_p), ("initial_guess_len", C.c_uint64),
+                ("compute_error_bounds", C.c_int32), ("error_bounds_tolerance", C.c_double),
+                ("enable_profiling", C.c_int32), ("has_random_seed", C.c_int32), ("random_seed", C.c_uint64),
+                ("mode", C.c_int32), ("dominance", C.c_int32), ("residual_check", C.c_int32), ("reserved", C.c_int32)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("solution", C.POINTER(C.c_double)), ("solution_len", C.c_uint64), ("residual_norm", C.c_double),
+                ("iterations", C.c_uint64), ("converged", C.c_int32), ("has_error_bounds", C.c_int32),
+                ("error_upper_bound", C.c_double), ("has_stats", C.c_int32), ("total_time_ms", C.c_double),
+                ("matvec_count", C.c_uint64), ("memory_bytes", C.c_uint64), ("terms_computed", C.c_uint64),
+                ("series_converged", C.c_int32), ("last_term_norm", C.c_double), ("device_time_ms", C.c_double),
+                ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+def build(force: bool = False) -> str:
+    """Compile the library in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    if force:
+        subprocess.run(["make", "-C", PKG_DIR, "clean"], check=True, capture_output=True)
+    r = subprocess.run(["make", "-C", PKG_DIR, "-j8"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libsublinear_b200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, i32, f64 = C.c_void_p, C.c_uint64, C.c_int32, C.c_double
+    P = C.POINTER
+    sig = {
+        "sb200_abi_version": ([], i32),
+        "sb200_last_error": ([C.c_char_p, C.c_size_t], C.c_size_t),
+        "sb200_device_count": ([P(i32)], i32),
+        "sb200_set_device": ([i32], i32),
+        "sb200_get_device": ([P(i32)], i32),
+        "sb200_host_alloc": ([u64, P(vp)], i32),
+        "sb200_host_free": ([vp], i32),
+        "sb200_matrix_from_triplets": ([vp, vp, vp, u64, u64, u64, P(vp)], i32),
+        "sb200_matrix_from_triplets_ex": ([vp, vp, vp, u64, u64, u64, i32, P(vp)], i32),
+        "sb200_matrix_from_csr": ([vp, vp, vp, u64, u64, u64, P(vp)], i32),
+        "sb200_matrix_from_csr64": ([vp, vp, vp, u64, u64, u64, P(vp)], i32),
+        "sb200_matrix_from_dense": ([vp, u64, u64, P(vp)], i32),
+        "sb200_matrix_identity": ([u64, P(vp)], i32),
+        "sb200_matrix_diagonal": ([vp, u64, P(vp)], i32),
+        "sb200_matrix_free": ([vp], None),
+        "sb200_matrix_rows": ([vp, P(u64)], i32),
+        "sb200_matrix_cols": ([vp, P(u64)], i32),
+        "sb200_matrix_nnz": ([vp, P(u64)], i32),
+        "sb200_matrix_get": ([vp, u64, u64, P(f64), P(i32)], i32),
+        "sb200_matrix_is_diagonally_dominant": ([vp, i32, P(i32)], i32),
+        "sb200_matrix_diagonal_dominance_factor": ([vp, P(f64), P(i32)], i32),
+        "sb200_matrix_export_csr": ([vp, vp, vp, vp], i32),
+        "sb200_matrix_multiply_vector": ([vp, vp, u64, vp, u64], i32),
+        "sb200_matrix_multiply_vector_add": ([vp, vp, u64, vp, u64], i32),
+        "sb200_matrix_multiply_vector_dev": ([vp, vp, u64, vp, u64, i32, vp], i32),
+        "sb200_matrix_scale": ([vp, f64], i32),
+        "sb200_neumann_new": ([u64, f64, P(vp)], i32),
+        "sb200_neumann_default": ([P(vp)], i32),
+        "sb200_neumann_high_precision": ([P(vp)], i32),
+        "sb200_neumann_fast": ([P(vp)], i32),
+        "sb200_neumann_with_adaptive_truncation": ([vp, i32], i32),
+        "sb200_neumann_with_power_caching": ([vp, i32], i32),
+        "sb200_neumann_config": ([vp, P(u64), P(f64), P(i32), P(i32)], i32),
+        "sb200_solver_algorithm_name": ([vp], C.c_char_p),
+        "sb200_solver_free": ([vp], None),
+        "sb200_options_default": ([P(_Options)], None),
+        "sb200_options_high_precision": ([P(_Options)], None),
+        "sb200_options_fast": ([P(_Options)], None),
+        "sb200_options_streaming": ([P(_Options), u64], None),
+        "sb200_solve": ([vp, vp, vp, u64, P(_Options), P(_Result)], i32),
+        "sb200_solve_into": ([vp, vp, vp, u64, P(_Options), vp, P(_Result)], i32),
+        "sb200_solve_dev": ([vp, vp, vp, u64, P(_Options), vp, vp, P(_Result)], i32),
+        "sb200_result_free": ([P(_Result)], None),
+        "sb200_push_iterations_dev": ([vp, vp, u64, u64, vp, vp, vp, vp, P(C.c_float)], i32),
+        "sb200_solve_entry": ([vp, vp, u64, vp, u64, f64, u64, u64, u64, vp, vp], i32),
+        "sb200_pagerank_system": ([vp, vp, vp, u64, u64, f64, P(vp), vp], i32),
+        "sb200_gen_bench_csr": ([u64, f64, u64, u64, vp, vp, vp, vp, P(u64)], i32),
+        "sb200_comm_unique_id": ([vp], i32),
+        "sb200_comm_init": ([i32, i32, vp, i32, P(vp)], i32),
+        "sb200_comm_free": ([vp], None),
+        "sb200_partition_rows": ([u64, i32, i32, P(u64), P(u64)], i32),
+        "sb200_dist_matrix_from_csr": ([vp, u64, u64, u64, vp, vp, vp, P(vp)], i32),
+        "sb200_dist_solve": ([vp, vp, vp, vp, u64, P(_Options), vp, P(_Result)], i32),
+        "sb200_dist_push_iterations_dev": ([vp, vp, vp, u64, u64, vp, vp, P(C.c_float)], i32),
+    }
+    for name, (args, res) in sig.items():
+        f = getattr(L, name)  # AttributeError here = the library does not export what the header declares
+        f.argtypes = args
+        f.restype = res
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(2048)
+    lib().sb200_last_error(buf, len(buf))
+    return buf.value.decode(errors="replace")
+
+
+def _check(rc: int, result=None):
+    if rc != OK:
+        raise SolverError(rc, last_error(), result)
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def device_count() -> int:
+    n = C.c_int32()
+    _check(lib().sb200_device_count(C.byref(n)))
+    return n.value
+
+
+def set_device(dev: int):
+    _check(lib().sb200_set_device(dev))
+
+
+class PinnedArray:
+    """float64 numpy view over sb200_host_alloc memory (PCIe line-rate source / destination)."""
+
+    def __init__(self, n: int):
+        self._p = C.c_void_p()
+        _check(lib().sb200_host_alloc(max(n, 1) * 8, C.byref(self._p)))
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_double)), shape=(max(n, 1),))[:n]
+
+    def __del__(self):
+        if getattr(self, "_p", None) and _lib is not None:
+            _lib.sb200_host_free(self._p)
+            self._p = None
+
+
+@dataclass
+class SolverOptions:
+    """`SolverOptions` (src/solver/mod.rs:22-45) + this library's extensions (mode / dominance / residual_check)."""
+    tolerance: float = 1e-6
+    max_iterations: int = 1000
+    convergence_mode: int = 0
+    norm_type: int = 1
+    collect_stats: bool = False
+    streaming_interval: int = 0
+    initial_guess: np.ndarray | None = None
+    compute_error_bounds: bool = False
+    error_bounds_tolerance: float = 1e-8
+    enable_profiling: bool = False
+    random_seed: int | None = None
+    mode: int = MODE_CORRECT
+    dominance: int = DOMINANCE_ROW
+    residual_check: int = RESIDUAL_EVERY_5
+
+    @staticmethod
+    def _preset(fn, *a) -> "SolverOptions":
+        o = _Options()
+        fn(C.byref(o), *a)
+        return SolverOptions(o.tolerance, o.max_iterations, o.convergence_mode, o.norm_type, bool(o.collect_stats),
+                             o.streaming_interval, None, bool(o.compute_error_bounds), o.error_bounds_tolerance,
+                             bool(o.enable_profiling), None, o.mode, o.dominance, o.residual_check)
+
+    @staticmethod
+    def default():
+        return SolverOptions._preset(lib().sb200_options_default)
+
+    @staticmethod
+    def high_precision():
+        return SolverOptions._preset(lib().sb200_options_high_precision)
+
+    @staticmethod
+    def fast():
+        return SolverOptions._preset(lib().sb200_options_fast)
+
+    @staticmethod
+    def streaming(interval: int):
+        return SolverOptions._preset(lib().sb200_options_streaming, interval)
+
+    def _c(self, guess_ptr=None, guess_len=0):
+        o = _Options()
+        lib().sb200_options_default(C.byref(o))
+        o.tolerance, o.max_iterations = self.tolerance, self.max_iterations
+        o.convergence_mode, o.norm_type = self.convergence_mode, self.norm_type
+        o.collect_stats, o.streaming_interval = int(self.collect_stats), self.streaming_interval
+        o.compute_error_bounds, o.error_bounds_tolerance = int(self.compute_error_bounds), self.error_bounds_tolerance
+        o.enable_profiling = int(self.enable_profiling)
+        o.has_random_seed, o.random_seed = int(self.random_seed is not None), self.random_seed or 0
+        o.mode, o.dominance, o.residual_check = self.mode, self.dominance, self.residual_check
+        if guess_ptr is not None:
+            o.initial_guess, o.initial_guess_len = guess_ptr, guess_len
+        return o
+
+
+@dataclass
+class SolverResult:
+    """`SolverResult` (src/solver/mod.rs:121-138) + SolverStats / extension fields."""
+    solution: np.ndarray | None
+    residual_norm: float
+    iterations: int
+    converged: bool
+    error_upper_bound: float | None
+    matvec_count: int
+    total_time_ms: float
+    memory_bytes: int
+    terms_computed: int
+    series_converged: bool
+    last_term_norm: float
+    device_time_ms: float
+    kernel_launches: int
+    h2d_bytes: int
+    d2h_bytes: int
+
+    @staticmethod
+    def _from(r: _Result, solution):
+        return SolverResult(solution, r.residual_norm, int(r.iterations), bool(r.converged),
+                            r.error_upper_bound if r.has_error_bounds else None, int(r.matvec_count),
+                            r.total_time_ms, int(r.memory_bytes), int(r.terms_computed), bool(r.series_converged),
+                            r.last_term_norm, r.device_time_ms, int(r.kernel_launches), int(r.h2d_bytes),
+                            int(r.d2h_bytes))
+
+
+class SparseMatrix:
+    """`SparseMatrix` in CSR form (src/matrix/mod.rs:123-372), resident in HBM."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.sb200_matrix_free(self._h)
+            self._h = None
+
+    # constructors ------------------------------------------------------------------------------
+    @staticmethod
+    def from_triplets(rows, cols, vals, nrows, ncols, dup_policy=DUP_KEEP) -> "SparseMatrix":
+        r, c, v = _u64(rows), _u64(cols), _f64(vals)
+        h = C.c_void_p()
+        _check(lib().sb200_matrix_from_triplets_ex(_ptr(r), _ptr(c), _ptr(v), len(v), nrows, ncols, dup_policy,
+                                                   C.byref(h)))
+        return SparseMatrix(h)
+
+    @staticmethod
+    def from_csr(row_ptr, col_indices, values, nrows, ncols) -> "SparseMatrix":
+        ci = np.ascontiguousarray(col_indices, dtype=np.uint32)
+        v = _f64(values)
+        h = C.c_void_p()
+        rp = np.asarray(row_ptr)
+        if rp.dtype == np.uint32:
+            rp = np.ascontiguousarray(rp)
+            _check(lib().sb200_matrix_from_csr(_ptr(rp), _ptr(ci), _ptr(v), nrows, ncols, len(v), C.byref(h)))
+        else:
+            rp = _u64(rp)
+            _check(lib().sb200_matrix_from_csr64(_ptr(rp), _ptr(ci), _ptr(v), nrows, ncols, len(v), C.byref(h)))
+        return SparseMatrix(h)
+
+    @staticmethod
+    def from_dense(a) -> "SparseMatrix":
+        a = _f64(a)
+        h = C.c_void_p()
+        _check(lib().sb200_matrix_from_dense(_ptr(a), a.shape[0], a.shape[1], C.byref(h)))
+        return SparseMatrix(h)
+
+    @staticmethod
+    def identity(n) -> "SparseMatrix":
+        h = C.c_void_p()
+        _check(lib().sb200_matrix_identity(n, C.byref(h)))
+        return SparseMatrix(h)
+
+    @staticmethod
+    def diagonal(d) -> "SparseMatrix":
+        d = _f64(d)
+        h = C.c_void_p()
+        _check(lib().sb200_matrix_diagonal(_ptr(d), len(d), C.byref(h)))
+        return SparseMatrix(h)
+
+    @staticmethod
+    def pagerank_system(src, dst, n, alpha=0.85, weights=None):
+        """computePageRank's system (src/core/solver.ts:664-722): returns (S, rhs)."""
+        s, d = _u64(src), _u64(dst)
+        w = None if weights is None else _f64(weights)
+        rhs = np.zeros(n)
+        h = C.c_void_p()
+        _check(lib().sb200_pagerank_system(_ptr(s), _ptr(d), _ptr(w), len(s), n, alpha, C.byref(h), _ptr(rhs)))
+        return SparseMatrix(h), rhs
+
+    # Matrix trait ------------------------------------------------------------------------------
+    def _dim(self, fn):
+        out = C.c_uint64()
+        _check(fn(self._h, C.byref(out)))
+        return out.value
+
+    def rows(self):
+        return self._dim(lib().sb200_matrix_rows)
+
+    def cols(self):
+        return self._dim(lib().sb200_matrix_cols)
+
+    def nnz(self):
+        return self._dim(lib().sb200_matrix_nnz)
+
+    def is_square(self):
+        return self.rows() == self.cols()
+
+    def get(self, row, col):
+        v, p = C.c_double(), C.c_int32()
+        _check(lib().sb200_matrix_get(self._h, row, col, C.byref(v), C.byref(p)))
+        return v.value if p.value else None
+
+    def is_diagonally_dominant(self, dominance=DOMINANCE_ROW):
+        out = C.c_int32()
+        _check(lib().sb200_matrix_is_diagonally_dominant(self._h, dominance, C.byref(out)))
+        return bool(out.value)
+
+    def diagonal_dominance_factor(self):
+        f, p = C.c_double(), C.c_int32()
+        _check(lib().sb200_matrix_diagonal_dominance_factor(self._h, C.byref(f), C.byref(p)))
+        return f.value if p.value else None
+
+    def multiply_vector(self, x, ylen=None):
+        x = _f64(x)
+        y = np.zeros(self.rows() if ylen is None else ylen)
+        _check(lib().sb200_matrix_multiply_vector(self._h, _ptr(x), len(x), _ptr(y), len(y)))
+        return y
+
+    def multiply_vector_add(self, x, y):
+        x, y = _f64(x), _f64(y).copy()
+        _check(lib().sb200_matrix_multiply_vector_add(self._h, _ptr(x), len(x), _ptr(y), len(y)))
+        return y
+
+    def multiply_vector_dev(self, x_ptr, xlen, y_ptr, ylen, accumulate=False, stream=0):
+        _check(lib().sb200_matrix_multiply_vector_dev(self._h, x_ptr, xlen, y_ptr, ylen, int(accumulate), stream))
+
+    def scale(self, factor):
+        _check(lib().sb200_matrix_scale(self._h, factor))
+
+    def to_csr(self):
+        n, nnz = self.rows(), self.nnz()
+        rp, ci, v = np.zeros(n + 1, np.uint64), np.zeros(nnz, np.uint32), np.zeros(nnz)
+        _check(lib().sb200_matrix_export_csr(self._h, _ptr(rp), _ptr(ci), _ptr(v)))
+        return rp, ci, v
+
+    def to_triplets(self):
+        rp, ci, v = self.to_csr()
+        rows = np.repeat(np.arange(self.rows(), dtype=np.uint64), np.diff(rp).astype(np.int64))
+        return rows, ci.astype(np.uint64), v
+
+
+class NeumannSolver:
+    """`NeumannSolver` (src/solver/neumann.rs:24-93, 469-555)."""
+
+    def __init__(self, max_terms: int = 50, series_tolerance: float = 1e-8, _handle=None):
+        if _handle is None:
+            _handle = C.c_void_p()
+            _check(lib().sb200_neumann_new(max_terms, series_tolerance, C.byref(_handle)))
+        self._h = _handle
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.sb200_solver_free(self._h)
+            self._h = None
+
+    @staticmethod
+    def _mk(fn):
+        h = C.c_void_p()
+        _check(fn(C.byref(h)))
+        return NeumannSolver(_handle=h)
+
+    @staticmethod
+    def new(max_terms, series_tolerance):
+        return NeumannSolver(max_terms, series_tolerance)
+
+    @staticmethod
+    def default():
+        return NeumannSolver._mk(lib().sb200_neumann_default)
+
+    @staticmethod
+    def high_precision():
+        return NeumannSolver._mk(lib().sb200_neumann_high_precision)
+
+    @staticmethod
+    def fast():
+        return NeumannSolver._mk(lib().sb200_neumann_fast)
+
+    def with_adaptive_truncation(self, enable):
+        _check(lib().sb200_neumann_with_adaptive_truncation(self._h, int(enable)))
+        return self
+
+    def with_power_caching(self, enable):
+        _check(lib().sb200_neumann_with_power_caching(self._h, int(enable)))
+        return self
+
+    def config(self):
+        mt, tol, ad, cp = C.c_uint64(), C.c_double(), C.c_int32(), C.c_int32()
+        _check(lib().sb200_neumann_config(self._h, C.byref(mt), C.byref(tol), C.byref(ad), C.byref(cp)))
+        return {"max_terms": mt.value, "series_tolerance": tol.value, "adaptive_truncation": bool(ad.value),
+                "cache_powers": bool(cp.value)}
+
+    def algorithm_name(self):
+        return lib().sb200_solver_algorithm_name(self._h).decode()
+
+    def solve(self, matrix: SparseMatrix, b, options: SolverOptions | None = None, out=None) -> SolverResult:
+        """`solver.solve(&matrix, &b, &options)`: host vectors in, host solution out.
+        `out` (optional float64 array, e.g. PinnedArray.array) receives the solution in place."""
+        options = options or SolverOptions()
+        b = _f64(b)
+        guess = None if options.initial_guess is None else _f64(options.initial_guess)
+        o = options._c(None if guess is None else guess.ctypes.data, 0 if guess is None else len(guess))
+        r = _Result()
+        if out is not None:
+            rc = lib().sb200_solve_into(self._h, matrix._h, _ptr(b), len(b), C.byref(o), _ptr(out), C.byref(r))
+            res = SolverResult._from(r, out)
+        else:
+            rc = lib().sb200_solve(self._h, matrix._h, _ptr(b), len(b), C.byref(o), C.byref(r))
+            sol = None
+            if r.solution:
+                sol = np.ctypeslib.as_array(r.solution, shape=(max(int(r.solution_len), 1),))[:int(r.solution_len)].copy()
+            res = SolverResult._from(r, sol)
+            lib().sb200_result_free(C.byref(r))
+        _check(rc, res)
+        return res
+
+    def solve_dev(self, matrix: SparseMatrix, b_ptr: int, n: int, x_ptr: int, options: SolverOptions | None = None,
+                  stream: int = 0, guess_ptr: int | None = None) -> SolverResult:
+        """Inputs/outputs already resident in HBM (raw device pointers, e.g. torch tensor.data_ptr())."""
+        options = options or SolverOptions()
+        o = options._c(guess_ptr, n if guess_ptr else 0)
+        r = _Result()
+        rc = lib().sb200_solve_dev(self._h, matrix._h, b_ptr, n, C.byref(o), x_ptr, stream, C.byref(r))
+        res = SolverResult._from(r, None)
+        _check(rc, res)
+        return res
+
+
+def push_iterations_dev(matrix: SparseMatrix, b_ptr: int, n: int, nterms: int, x_ptr: int = 0, t_ptr: int = 0,
+                        stream: int = 0):
+    """Bare recurrence on device pointers; returns (per-term norms, CUDA-event ms of the nterms launches)."""
+    norms = np.zeros(max(nterms, 1))
+    ms = C.c_float()
+    _check(lib().sb200_push_iterations_dev(matrix._h, b_ptr, n, nterms, x_ptr or None, t_ptr or None, _ptr(norms),
+                                           stream or None, C.byref(ms)))
+    return norms[:nterms], ms.value
+
+
+def solve_entry(matrix: SparseMatrix, b, rows, eps=0.01, nwalks=0, max_steps=0, seed=0):
+    """Batched single-entry estimates x[rows[q]] by absorbing random walks; returns (estimate, variance)."""
+    b, q = _f64(b), _u64(rows)
+    est, var = np.zeros(len(q)), np.zeros(len(q))
+    _check(lib().sb200_solve_entry(matrix._h, _ptr(b), len(b), _ptr(q), len(q), eps, nwalks, max_steps, seed,
+                                   _ptr(est), _ptr(var)))
+    return est, var
+
+
+def gen_bench_csr(size, sparsity, row0=0, row1=None):
+    """create_test_matrix / create_test_rhs (benches/performance_benchmarks.rs:12-43) as CSR, rows [row0,row1)."""
+    row1 = size if row1 is None else row1
+    nnz = C.c_uint64()
+    _check(lib().sb200_gen_bench_csr(size, sparsity, row0, row1, None, None, None, None, C.byref(nnz)))
+    rp = np.zeros(row1 - row0 + 1, np.uint64)
+    ci, v, b = np.zeros(nnz.value, np.uint32), np.zeros(nnz.value), np.zeros(row1 - row0)
+    _check(lib().sb200_gen_bench_csr(size, sparsity, row0, row1, _ptr(rp), _ptr(ci), _ptr(v), _ptr(b), C.byref(nnz)))
+    return rp, ci, v, b
+
+
+def partition_rows(nrows: int, world: int, rank: int):
+    r0, r1 = C.c_uint64(), C.c_uint64()
+    _check(lib().sb200_partition_rows(nrows, world, rank, C.byref(r0), C.byref(r1)))
+    return r0.value, r1.value
+
+
+class Comm:
+    """One rank of a row-partitioned multi-GPU job (NCCL communicator inside the library)."""
+
+    def __init__(self, rank: int, world: int, unique_id: bytes, device: int):
+        assert len(unique_id) == UNIQUE_ID_BYTES
+        self.rank, self.world, self.device = rank, world, device
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(unique_id, UNIQUE_ID_BYTES)
+        _check(lib().sb200_comm_init(rank, world, buf, device, C.byref(self._h)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+        _check(lib().sb200_comm_unique_id(buf))
+        return buf.raw
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.sb200_comm_free(self._h)
+            self._h = None
+
+    def matrix_from_csr(self, n_global, row0, row1, row_ptr, col_indices, values) -> SparseMatrix:
+        rp, ci, v = _u64(row_ptr), np.ascontiguousarray(col_indices, dtype=np.uint32), _f64(values)
+        h = C.c_void_p()
+        _check(lib().sb200_dist_matrix_from_csr(self._h, n_global, row0, row1, _ptr(rp), _ptr(ci), _ptr(v), C.byref(h)))
+        return SparseMatrix(h)
+
+    def solve(self, solver: NeumannSolver, m_local: SparseMatrix, b_local, options: SolverOptions | None = None):
+        options = options or SolverOptions()
+        b = _f64(b_local)
+        x = np.zeros(len(b))
+        o = options._c()
+        r = _Result()
+        rc = lib().sb200_dist_solve(self._h, solver._h, m_local._h, _ptr(b), len(b), C.byref(o), _ptr(x), C.byref(r))
+        res = SolverResult._from(r, x)
+        _check(rc, res)
+        return res
+
+    def push_iterations_dev(self, m_local: SparseMatrix, b_ptr: int, nlocal: int, nterms: int, x_ptr: int = 0):
+        norms = np.zeros(max(nterms, 1))
+        ms = C.c_float()
+        _check(lib().sb200_dist_push_iterations_dev(self._h, m_local._h, b_ptr, nlocal, nterms, x_ptr or None,
+                                                    _ptr(norms), C.byref(ms)))
+        return norms[:nterms], ms.value
