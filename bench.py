@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py — push-iteration throughput (processed nnz/s) of the Neumann / forward-push path.
+
+Workload (BASELINE.json `metric`): gen_bench(10 000 000, 1e-6) = the reference's own Criterion generator
+(benches/performance_benchmarks.rs:12-43): n = 10 M, nnz ~ 100 M, uniform-random columns, b_i = 1 + 0.001 i.
+A "step" is one full NeumannSolver::solve (default solver 50 terms / 1e-8, default options tolerance 1e-6,
+MODE_CORRECT, the reference's residual-every-5th-iteration cadence).
+  value : nnz x SpMV-equivalents (matvec_count) per second, inputs resident in HBM (sb200_solve_dev), CUDA-event timed
+  e2e   : the same through the host-pointer C-ABI call a drop-in user makes (sb200_solve_into): pinned host b in,
+          pinned host x out, H2D + D2H inside the timed region
+  roofline : fused push kernel, algorithmic bytes 12 nnz + 44 n + 4 per launch / average launch time (CUDA events
+          around every push launch inside the timed steps) vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : the oracle's restatement of the reference's rayon row-chunk SpMV (src/simd_ops.rs:202-239) inside
+          the same recurrence, all host cores, bounded sample
+N > 1 (torchrun, one rank per GPU): STRONG scaling on the same 10 M system — contiguous row blocks, one NCCL
+allgather of the term slice + a 2-double allreduce per term (sb200_dist_solve).
+`--impl reference`: the reference's CPU path (oracle port; no Rust toolchain in this image) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "sublinear-time-solver_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: (size, sparsity)  — gen_bench(size, sparsity), SURVEY.md §8(d)
+    "c3_n10M_nnz100M": (10_000_000, 1e-6),
+    "c2_n1M_nnz10M": (1_000_000, 1e-5),
+    "c5_n100M_nnz1B": (100_000_000, 1e-7),
+    "tiny_n100k": (100_000, 1e-4),
+    # best-case gather locality (SURVEY.md §8d asks for it next to the uniform-random headline): same row length and
+    # values, columns within +-64 of the diagonal; single GPU only, generated with numpy
+    "banded_n10M_nnz100M": (10_000_000, 1e-6),
+}
+METRIC = "push-iter nnz/sec at n=10M nnz=100M"
+UNIT = "nnz/s"
+
+
+def algorithmic_bytes_push(n, nnz):
+    return 12 * nnz + 44 * n + 4        # SURVEY.md §8(d), BASELINE.md §3
+
+
+def measured_peak():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class CpuPath:
+    """The reference's CPU path restated (oracle/, rebuilt -O3 -march=native on THIS host): the rayon-style
+    row-chunk parallel SpMV (src/simd_ops.rs:202-239) inside the push recurrence, all host cores."""
+
+    def __init__(self, size, sparsity):
+        import ctypes as C
+        import tempfile
+        import numpy as np
+        from oracle import oracle as O
+        self.C, self.O = C, O
+        self.L = O.lib(fast=True, out_dir=tempfile.mkdtemp(prefix="sb200_oracle_"))
+        self.raw = O._Csr()
+        self.b = np.zeros(size)
+        rc = self.L.orc_gen_bench_csr(size, sparsity, 0, size, C.byref(self.raw),
+                                      self.b.ctypes.data_as(C.POINTER(C.c_double)))
+        assert rc == 0
+        self.nnz = int(self.raw.nnz)
+        self.cores = os.cpu_count() or 1
+
+    def run(self, iters):
+        C = self.C
+        secs = self.L.orc_push_iterations(C.byref(self.raw), self.b.ctypes.data_as(C.POINTER(C.c_double)), iters,
+                                          self.O.SPMV_PARALLEL, self.cores, None, None, None)
+        return self.nnz * iters / secs, secs
+
+    def close(self):
+        self.L.orc_csr_free(self.C.byref(self.raw))
+
+
+def cpu_sample_shape(size, sparsity):
+    # bounded: the CPU arm uses the workload itself up to 10M rows, a 10M-row system of the same generator above
+    if size > 10_000_000:
+        return 10_000_000, sparsity * size / 10_000_000
+    return size, sparsity
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores. The reference is
+    Rust (no toolchain here, so no oracle/_ref): the arm is the oracle port (kind "port"), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    size, sparsity = WORKLOADS[args.workload]
+    s_size, s_sparsity = cpu_sample_shape(size, sparsity)
+    cpu = CpuPath(s_size, s_sparsity)
+    sample = (f"gen_bench({s_size}, {s_sparsity:g}) nnz={cpu.nnz}, {args.cpu_iters} push iterations "
+              f"(SpMV + diagonal scale + term/solution update + norm) per step, OpenMP row chunks on {cpu.cores} threads")
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, secs = cpu.run(args.cpu_iters)
+        if i >= args.warmup:
+            vals.append((v, secs))
+    cpu.close()
+    total_s = sum(s for _, s in vals)
+    value = cpu.nnz * args.cpu_iters * len(vals) / total_s
+    ms = 1e3 * total_s / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "n": s_size, "nnz": cpu.nnz,
+                       "generator": "gen_bench(size, sparsity) = benches/performance_benchmarks.rs:12-43, uniform-random columns",
+                       "step": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def gen_banded(n, k, w, seed=1):
+    """Banded companion of gen_bench: a_ii = 10 + 0.01 i, k-1 positive off-diagonals of the same magnitude law
+    (< a_ii / (2k)) at columns i + d, 1 <= |d| <= w (reflected at the borders); rows sorted by column."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    i = np.arange(n, dtype=np.int64)[:, None]
+    d = rng.integers(1, w + 1, size=(n, k - 1)) * rng.choice(np.array([-1, 1]), size=(n, k - 1))
+    c = i + d
+    c = np.where((c < 0) | (c >= n), i - d, c)          # fold back inside, never onto the diagonal
+    diag = 10.0 + 0.01 * np.arange(n)
+    vals = rng.random((n, k - 1)) * (diag / (2.0 * k))[:, None]
+    cols = np.concatenate([i, c], axis=1)
+    vals = np.concatenate([diag[:, None], vals], axis=1)
+    order = np.argsort(cols, axis=1, kind="stable")
+    cols = np.take_along_axis(cols, order, axis=1).astype(np.uint32).ravel()
+    vals = np.take_along_axis(vals, order, axis=1).ravel()
+    rp = np.arange(n + 1, dtype=np.uint64) * k
+    return rp, cols, vals, 1.0 + 0.001 * np.arange(n)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3_n10M_nnz100M", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-iters", type=int, default=5)
+    ap.add_argument("--cpu-baseline-iters", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="correct", choices=["correct", "ref_compat"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import sublinear_b200 as sb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3:
+        args.warmup = 3
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    sb.set_device(local_rank)
+    dist = world > 1
+    if dist:
+        import torch.distributed as td
+        td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    size, sparsity = WORKLOADS[args.workload]
+    mode = sb.MODE_CORRECT if args.mode == "correct" else sb.MODE_REF_COMPAT
+    opts = sb.SolverOptions(mode=mode, enable_profiling=True, collect_stats=True)
+    solver = sb.NeumannSolver.default()
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            td.barrier()
+            torch.cuda.synchronize()
+
+    t_gen = time.perf_counter()
+    if args.workload.startswith("banded"):
+        if dist:
+            raise SystemExit("the banded workload is single-GPU only")
+        rp, ci, v, b = gen_banded(size, 10, 64)
+        nnz_total, n_local = len(v), size
+        m = sb.SparseMatrix.from_csr(rp, ci, v, size, size)
+        comm = None
+    elif not dist:
+        rp, ci, v, b = sb.gen_bench_csr(size, sparsity)
+        nnz_total, n_local = len(v), size
+        m = sb.SparseMatrix.from_csr(rp, ci, v, size, size)
+        comm = None
+    else:
+        uid = [sb.Comm.unique_id() if rank == 0 else None]
+        td.broadcast_object_list(uid, src=0)
+        comm = sb.Comm(rank, world, uid[0], local_rank)
+        r0, r1 = sb.partition_rows(size, world, rank)
+        rp, ci, v, b = sb.gen_bench_csr(size, sparsity, r0, r1)      # rows are independently seeded: each rank builds its own
+        n_local = r1 - r0
+        m = comm.matrix_from_csr(size, r0, r1, rp, ci, v)
+        t = torch.tensor([len(v)], dtype=torch.int64, device="cuda")
+        td.all_reduce(t)
+        nnz_total = int(t.item())
+    del rp, ci, v
+    t_gen = time.perf_counter() - t_gen
+
+    # inputs: device-resident b for `value`, pinned host b / x for `e2e`
+    b_dev = torch.tensor(b, device="cuda")
+    x_dev = torch.empty_like(b_dev)
+    b_pin = torch.from_numpy(b).pin_memory()
+    x_pin = torch.empty(n_local, dtype=torch.float64).pin_memory()
+
+    def step_dev():
+        if not dist:
+            return solver.solve_dev(m, b_dev.data_ptr(), n_local, x_dev.data_ptr(), opts, stream)
+        return _dist_step(b_dev.data_ptr(), x_dev.data_ptr())
+
+    def _dist_step(bp, xp):
+        import ctypes as C
+        o = opts._c()
+        r = sb._Result()
+        rc = sb.lib().sb200_dist_solve(comm._h, solver._h, m._h, bp, n_local, C.byref(o), xp, C.byref(r))
+        res = sb.SolverResult._from(r, None)
+        sb._check(rc, res)
+        return res
+
+    def step_e2e():
+        if not dist:
+            return solver.solve(m, b_pin.numpy(), opts, out=x_pin.numpy())
+        return _dist_step(b_pin.data_ptr(), x_pin.data_ptr())
+
+    # ---- value: device-resident, CUDA events on the launching stream, max over ranks ----
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    results = []
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        results.append(step_dev())
+    ev1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    wall = (t_wall1 - t_wall0) * 1e3
+    if dist:
+        # the row-partitioned path runs on the communicator's own stream (torch events on the current stream do not
+        # see it); its calls are synchronous, so the barrier-to-barrier wall clock, max over ranks, is the step time
+        ms_total = wall
+        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        ms_total = float(t.item())
+    r_last = results[-1]
+    matvecs = sum(r.matvec_count for r in results)
+    value = nnz_total * matvecs / (ms_total * 1e-3)
+    launches = sum(r.kernel_launches for r in results)
+
+    # ---- roofline of the dominant kernel (fused push), live from the timed region ----
+    push_ms = sum(r.push_kernel_ms for r in results)
+    push_cnt = sum(r.push_kernel_count for r in results)
+    res_ms = sum(r.resid_kernel_ms for r in results)
+    res_cnt = sum(r.resid_kernel_count for r in results)
+    nnz_local = m.nnz()
+    peak, peak_src = measured_peak()
+    roofline = None
+    if push_cnt:
+        t_push = push_ms / push_cnt * 1e-3
+        alg = algorithmic_bytes_push(n_local, nnz_local) + (8 * (size - n_local) if dist else 0)
+        ach = alg / t_push / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "kernel": "tile_kernel<EPI_PUSH>", "avg_launch_us": t_push * 1e6,
+                    "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                    "frac_of_nominal_8TBs": ach / 8000.0, "push_share_of_step": push_ms / (ms_total if not dist else wall),
+                    "resid_kernel_avg_us": (res_ms / res_cnt * 1e3) if res_cnt else None,
+                    "nnz_per_s_push_kernel": nnz_local / t_push}
+
+    # ---- e2e: host buffers through the C-ABI solve call, copies inside the timed region ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_results = [step_e2e() for _ in range(args.steps)]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = nnz_total * sum(r.matvec_count for r in e2e_results) / e2e_s
+
+    # sanity of what was timed: the solve converged and ||Ax-b||/||b|| is small (library SpMV, bit-checked in tests)
+    rel_res = None
+    if not dist:
+        y = torch.empty_like(b_dev)
+        m.multiply_vector_dev(x_dev.data_ptr(), n_local, y.data_ptr(), n_local, False, stream)
+        torch.cuda.synchronize()
+        rel_res = float(torch.linalg.vector_norm(y - b_dev) / torch.linalg.vector_norm(b_dev))
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        s_size, s_sparsity = cpu_sample_shape(size, sparsity)
+        cpu = CpuPath(s_size, s_sparsity)
+        cpu.run(2)
+        v, secs = cpu.run(args.cpu_baseline_iters)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cpu.cores, "kind": "port",
+                        "sample": f"oracle restatement of parallel_matrix_vector_multiply (src/simd_ops.rs:202-239) in the push "
+                                  f"recurrence, gen_bench({s_size}, {s_sparsity:g}) nnz={cpu.nnz}, "
+                                  f"{args.cpu_baseline_iters} iterations, {secs:.2f} s"}
+        cpu.close()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "n": size, "nnz": nnz_total,
+                       "generator": ("banded companion of gen_bench: columns within +-64 of the diagonal (best-case locality)"
+                                     if args.workload.startswith("banded") else
+                                     "gen_bench(size, sparsity) = benches/performance_benchmarks.rs:12-43, uniform-random columns"),
+                       "step": "one NeumannSolver::default().solve (50 terms / 1e-8, tolerance 1e-6, residual every 5th iteration)",
+                       "mode": args.mode, "terms_per_step": r_last.terms_computed, "matvecs_per_step": r_last.matvec_count,
+                       "iterations_per_step": r_last.iterations, "converged": r_last.converged,
+                       "l2_policy": "inputs larger than L2 (1.2 GB CSR stream per SpMV vs 126 MB L2), no flush",
+                       "parallelism": "single GPU" if not dist else f"row blocks x{world}, NCCL allgather of the term slice per term",
+                       "rel_residual": rel_res, "setup_s": t_gen},
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_local * world if dist else 8 * n_local,
+                    "d2h_bytes_per_step": 8 * n_local * world if dist else 8 * n_local, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "api": "sb200_solve_into (host b -> host x)" if not dist else "sb200_dist_solve (host b_local -> host x_local)"},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if dist:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

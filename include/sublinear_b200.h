@@ -120,6 +120,12 @@ typedef struct sb200_result {
     double device_time_ms;         /* CUDA-event time of the iteration loop (kernels only) */
     uint64_t kernel_launches;      /* launches of this library's kernels during the call */
     uint64_t h2d_bytes, d2h_bytes; /* bytes moved across PCIe during the call */
+    /* filled when options.enable_profiling (ProfileData in the reference, src/types.rs:236-251, is never filled):
+     * CUDA-event time of the launches that did work, per kernel kind */
+    double push_kernel_ms;         /* fused push kernels (one per term after the first) */
+    uint64_t push_kernel_count;
+    double resid_kernel_ms;        /* residual kernels (every 5th iteration + final) */
+    uint64_t resid_kernel_count;
 } sb200_result;
 
 /* ---------------------------------------------------------------------------------------------- */

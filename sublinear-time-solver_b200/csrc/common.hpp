@@ -79,10 +79,11 @@ struct TileDesc {
 
 // Tile geometry (one instantiation of the kernel template each).
 struct TileCfg {
-    int threads;  // CTA size = max rows per tile
+    int threads;  // CTA size
+    int rows;     // max rows per tile (<= threads)
     int cap;      // max nnz staged per tile; a single row above it is a "long row" tile
 };
-constexpr int kNumTileCfgs = 3;
+constexpr int kNumTileCfgs = 6;
 extern const TileCfg kTileCfgs[kNumTileCfgs];
 int default_tile_cfg();
 
@@ -118,7 +119,9 @@ struct TileKernelArgs {
     uint32_t nrows;
     // vectors
     const double *xin;    // gather source (term / solution / x)
-    const double *xin_own; // value of xin for local row i is xin_own[i] (== xin + row offset when distributed)
+    const double *xin_own; // value of xin for local row i is xin_own[i] (== xin + row_base)
+    uint32_t row_base;    // global column index of local row 0 (0 unless row-partitioned)
+    uint64_t xin_len;     // length of the gather source (matrix columns)
     double *out;          // SPMV: y ; PUSH: new term (indexed by local row)
     double *sol;          // PUSH: solution (read+write)
     const double *dinv;   // PUSH
@@ -133,6 +136,7 @@ struct TileKernelArgs {
     int identity_res;     // PUSH: also accumulate ||D o t'||^2
     int defer_tail;       // distributed: only publish the local sums; a later kernel runs the loop logic
     double *norm_log;     // optional: norm_log[it] = ||t_it||^2 (bare recurrence)
+    unsigned long long *phase_log;  // debug ($SUBLINEAR_B200_PHASE_LOG=1): per-phase cycles of thread 0, summed over CTAs
 };
 
 // launchers (kernels.cu). grid = 0 -> persistent grid sized from occupancy.

@@ -75,11 +75,11 @@ void matrix_release_ws(sb200_matrix *m, std::unique_ptr<Workspace> ws) {
 // Group rows into tiles of <= threads rows and <= cap non-zeros; a row above cap becomes its own tile.
 static void build_tiles(const uint32_t *row_ptr, uint64_t nrows, TileCfg cfg, std::vector<TileDesc> &tiles) {
     tiles.clear();
-    tiles.reserve(nrows / (size_t)cfg.threads + 16);
+    tiles.reserve(nrows / (size_t)cfg.rows + 16);
     uint64_t r = 0;
     while (r < nrows) {
         uint64_t r1 = r;
-        const uint64_t rmax = std::min<uint64_t>(nrows, r + (uint64_t)cfg.threads);
+        const uint64_t rmax = std::min<uint64_t>(nrows, r + (uint64_t)cfg.rows);
         const uint64_t base = row_ptr[r];
         while (r1 < rmax && (uint64_t)row_ptr[r1 + 1] - base <= (uint64_t)cfg.cap) r1++;
         if (r1 == r) r1 = r + 1;  // long row
@@ -172,6 +172,8 @@ void fill_tile_args(const sb200_matrix *m, TileKernelArgs &a) {
     a.tiles = m->d_tiles.p;
     a.ntiles = m->ntiles;
     a.nrows = (uint32_t)m->nrows;
+    a.row_base = (uint32_t)m->row_base;
+    a.xin_len = m->ncols;
 }
 
 int32_t matrix_spmv_dev(const sb200_matrix *m, const double *x_dev, double *y_dev, int accumulate, cudaStream_t st) {

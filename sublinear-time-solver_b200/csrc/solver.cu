@@ -112,6 +112,36 @@ int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev
     base.partials = ws.partials.p;
     base.identity_res = identity;
 
+    // optional per-launch events (options.enable_profiling): which launches did work is known after the loop
+    struct ProfEv {
+        cudaEvent_t e0, e1;
+        int kind;  // 1 push, 2 residual
+        uint64_t it;
+        int force;
+    };
+    std::vector<ProfEv> prof;
+    const bool profiling = opt->enable_profiling != 0;
+    struct ProfCleanup {
+        std::vector<ProfEv> &v;
+        ~ProfCleanup() {
+            for (auto &p : v) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+        }
+    } prof_cleanup{prof};
+    auto prof_begin = [&](int kind, uint64_t it, int force) -> int32_t {
+        if (!profiling) return SB200_OK;
+        ProfEv p{nullptr, nullptr, kind, it, force};
+        SB_CUDA(cudaEventCreate(&p.e0));
+        SB_CUDA(cudaEventCreate(&p.e1));
+        SB_CUDA(cudaEventRecord(p.e0, st));
+        prof.push_back(p);
+        return SB200_OK;
+    };
+    auto prof_end = [&]() -> int32_t {
+        if (!profiling) return SB200_OK;
+        SB_CUDA(cudaEventRecord(prof.back().e1, st));
+        return SB200_OK;
+    };
+
     auto enqueue_resid = [&](uint64_t it, int last, int force) -> int32_t {
         TileKernelArgs a = base;
         a.xin = x_out_dev;
@@ -122,7 +152,9 @@ int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev
         a.force = force;
         a.identity_res = 0;
         launches++;
-        return launch_tile_kernel(cfg, EPI_RESID, a, st);
+        SB_TRY(prof_begin(2, it, force));
+        SB_TRY(launch_tile_kernel(cfg, EPI_RESID, a, st));
+        return prof_end();
     };
     auto read_ctl = [&]() -> int32_t {
         SB_CUDA(cudaMemcpyAsync(ws.h_ctl, ws.ctl.p, sizeof(LoopCtl), cudaMemcpyDeviceToHost, st));
@@ -183,7 +215,9 @@ int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev
                 a.dinv = dinv;
                 a.it = (uint32_t)it;
                 a.last_in_iter = !resid_due;
+                SB_TRY(prof_begin(1, it, 0));
                 SB_TRY(launch_tile_kernel(cfg, EPI_PUSH, a, st));
+                SB_TRY(prof_end());
                 launches++;
                 if (resid_due) SB_TRY(enqueue_resid(it, 1, 0));
             }
@@ -236,6 +270,14 @@ int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev
     SB_CUDA(cudaEventElapsedTime(&dev_ms, ws.ev0, ws.ev1));
 
     const LoopCtl &c = *ws.h_ctl;
+    for (auto &p : prof) {  // launches past the end of the loop were no-ops: leave them out of the averages
+        const bool live = p.force || (p.kind == 1 ? p.it < c.terms : p.it < c.iterations);
+        if (!live) continue;
+        float ms = 0.f;
+        SB_CUDA(cudaEventElapsedTime(&ms, p.e0, p.e1));
+        if (p.kind == 1) { stats.push_ms += ms; stats.push_count++; }
+        else { stats.resid_ms += ms; stats.resid_count++; }
+    }
     stats.iterations = iterations;
     stats.terms = c.terms;
     stats.series_converged = c.sconv != 0;
@@ -316,6 +358,10 @@ static void fill_result(const sb200_solver *s, const sb200_options *opt, const S
     out->matvec_count = st.matvec;
     out->total_time_ms = total_ms;
     out->has_stats = opt->collect_stats != 0;
+    out->push_kernel_ms = st.push_ms;
+    out->push_kernel_count = st.push_count;
+    out->resid_kernel_ms = st.resid_ms;
+    out->resid_kernel_count = st.resid_count;
     out->has_error_bounds = 0;
     out->error_upper_bound = 0.0;
     // estimate_error_bounds (:321-347), evaluated on the final state (it only fires once series_converged)
@@ -546,6 +592,15 @@ int32_t sb200_push_iterations_dev(const sb200_matrix *m, const double *b_dev, ui
     base.norm_log = ws->norm_log.p;
     base.sol = x;
     base.dinv = m->d_dinv[0].p;
+    // debug aid: $SUBLINEAR_B200_PHASE_LOG=<thread index> prints the per-phase cycle breakdown of the push kernel
+    DevBuf<unsigned long long> plog;
+    if (const char *e = getenv("SUBLINEAR_B200_PHASE_LOG")) {
+        SB_TRY(plog.alloc(64));
+        unsigned long long init[64] = {0};
+        init[63] = (unsigned long long)atoll(e);
+        SB_CUDA(cudaMemcpyAsync(plog.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        base.phase_log = plog.p;
+    }
     SB_CUDA(cudaEventRecord(ws->ev0, st));
     for (uint64_t it = 1; it <= nterms; it++) {
         TileKernelArgs a = base;
@@ -563,6 +618,19 @@ int32_t sb200_push_iterations_dev(const sb200_matrix *m, const double *b_dev, ui
     if (elapsed_ms) SB_CUDA(cudaEventElapsedTime(elapsed_ms, ws->ev0, ws->ev1));
     if (term_norms)
         for (uint64_t k = 0; k < nterms; k++) term_norms[k] = std::sqrt(log[k + 1]);
+    if (plog.p) {
+        unsigned long long h[64];
+        SB_CUDA(cudaMemcpy(h, plog.p, sizeof(h), cudaMemcpyDeviceToHost));
+        const char *names[] = {"ring+tma_issue", "wait_cols+gather_issue", "load_rows", "cp_async_wait", "wait_vals",
+                               "barrier1", "product", "barrier2", "sum+epilogue", "fence+barrier3"};
+        unsigned long long tot = 0;
+        for (int i = 0; i < 10; i++) tot += h[i];
+        fprintf(stderr, "[sublinear_b200] push-kernel phase cycles (thread %llu, %llu CTA-launches, %llu tiles):\n", h[63], h[32],
+                (unsigned long long)m->ntiles * nterms);
+        for (int i = 0; i < 10; i++)
+            fprintf(stderr, "  %-24s %6.1f %%  %8.0f cycles/tile\n", names[i], 100.0 * h[i] / (double)tot,
+                    (double)h[i] / ((double)m->ntiles * nterms));
+    }
     return SB200_OK;
 }
 

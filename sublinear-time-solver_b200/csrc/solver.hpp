@@ -17,6 +17,8 @@ struct SolveStats {
     bool converged = false, series_converged = false, nonfinite = false;
     double residual_norm = 0, last_term_norm = 0, rhs_norm = 0;
     float device_ms = 0;
+    double push_ms = 0, resid_ms = 0;   // per-kind CUDA-event totals (enable_profiling)
+    uint64_t push_count = 0, resid_count = 0;
 };
 
 int32_t validate_options(const sb200_options *opt);

@@ -57,7 +57,9 @@ class _Result(C.Structure):
                 ("error_upper_bound", C.c_double), ("has_stats", C.c_int32), ("total_time_ms", C.c_double),
                 ("matvec_count", C.c_uint64), ("memory_bytes", C.c_uint64), ("terms_computed", C.c_uint64),
                 ("series_converged", C.c_int32), ("last_term_norm", C.c_double), ("device_time_ms", C.c_double),
-                ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("push_kernel_ms", C.c_double), ("push_kernel_count", C.c_uint64),
+                ("resid_kernel_ms", C.c_double), ("resid_kernel_count", C.c_uint64)]
 
 
 def build(force: bool = False) -> str:
@@ -269,6 +271,10 @@ class SolverResult:
     kernel_launches: int
     h2d_bytes: int
     d2h_bytes: int
+    push_kernel_ms: float = 0.0
+    push_kernel_count: int = 0
+    resid_kernel_ms: float = 0.0
+    resid_kernel_count: int = 0
 
     @staticmethod
     def _from(r: _Result, solution):
@@ -276,7 +282,8 @@ class SolverResult:
                             r.error_upper_bound if r.has_error_bounds else None, int(r.matvec_count),
                             r.total_time_ms, int(r.memory_bytes), int(r.terms_computed), bool(r.series_converged),
                             r.last_term_norm, r.device_time_ms, int(r.kernel_launches), int(r.h2d_bytes),
-                            int(r.d2h_bytes))
+                            int(r.d2h_bytes), r.push_kernel_ms, int(r.push_kernel_count), r.resid_kernel_ms,
+                            int(r.resid_kernel_count))
 
 
 class SparseMatrix:

@@ -29,7 +29,7 @@ def dense(O, a):
     return O.Csr.from_dense(np.asarray(a, dtype=np.float64))
 
 
-def assert_same_result(r, o, *, exact_solution=True):
+def assert_same_result(r, o, *, exact_solution=True, residual_atol=1e-18):
     assert r.iterations == o.iterations and r.terms_computed == o.terms_computed
     assert r.matvec_count == o.matvec_count
     assert r.converged == o.converged and r.series_converged == o.series_converged
@@ -37,7 +37,7 @@ def assert_same_result(r, o, *, exact_solution=True):
         assert np.array_equal(r.solution, o.solution)
     else:
         np.testing.assert_allclose(r.solution, o.solution, rtol=1e-12, atol=1e-300)
-    np.testing.assert_allclose(r.residual_norm, o.residual_norm, rtol=1e-9, atol=1e-18)
+    np.testing.assert_allclose(r.residual_norm, o.residual_norm, rtol=1e-9, atol=residual_atol)
     np.testing.assert_allclose(r.last_term_norm, o.last_term_norm, rtol=1e-11, atol=1e-300)
 
 
@@ -343,7 +343,9 @@ def test_pagerank_system_and_column_dominance(oracle):
     opt = sb.SolverOptions(dominance=sb.DOMINANCE_ROW_OR_COL, tolerance=1e-9)
     r = s.solve(Sg, rhs, opt)
     o = O.neumann_solve(So, rhs, dominance=O.DOM_ROW_OR_COL, max_terms=200, series_tolerance=1e-10, tolerance=1e-9)
-    assert_same_result(r, o, exact_solution=False)
+    # hub rows take the long-row path (tree order): at convergence A x - b cancels to ~1e-10, so the norms agree to
+    # rounding of the row sums (~eps * ||b||), not to 1e-9 relative
+    assert_same_result(r, o, exact_solution=False, residual_atol=1e-12 * float(np.linalg.norm(rhs)))
     # power iteration x <- rhs + alpha P^T x has the same fixed point
     P = So.to_scipy()
     assert np.linalg.norm(P @ r.solution - rhs) < 1e-8 and (r.solution > 0).all()
