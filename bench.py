@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -283,11 +283,16 @@ def main():
         return _dist_step(b_pin.data_ptr(), x_pin.data_ptr())
 
     # ---- value: device-resident, CUDA events on the launching stream, max over ranks ----
-    for _ in range(args.warmup):
-        step_dev()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()      # nvidia-smi needs ~0.5 s to deliver its first sample: started before the warm-up steps,
+        time.sleep(0.6)      # which put the same load on the GPU as the timed ones
+    for _ in range(args.warmup):
+        step_dev()
+    if rank == 0:
+        sampler.rows.clear() # keep the samples taken under load only
+    for _ in range(args.warmup):
+        step_dev()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     results = []
@@ -325,8 +330,15 @@ def main():
         t_push = push_ms / push_cnt * 1e-3
         alg = algorithmic_bytes_push(n_local, nnz_local) + (8 * (size - n_local) if dist else 0)
         ach = alg / t_push / 1e9
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "push_traffic.json"))).get(args.workload)
+            if tr and not dist:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "kernel": "tile_kernel<EPI_PUSH>", "avg_launch_us": t_push * 1e6,
+                    "traffic": traffic, "kernel": "warp_kernel<EPI_PUSH,256>", "avg_launch_us": t_push * 1e6,
                     "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                     "frac_of_nominal_8TBs": ach / 8000.0, "push_share_of_step": push_ms / (ms_total if not dist else wall),
                     "resid_kernel_avg_us": (res_ms / res_cnt * 1e3) if res_cnt else None,

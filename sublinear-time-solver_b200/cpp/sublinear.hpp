@@ -1,0 +1,224 @@
+// sublinear.hpp — C++17 host-side mirror of the reference crate's API for the Neumann / push path, over the C ABI
+// (include/sublinear_b200.h). Same names, argument meaning and error behaviour as the Rust types:
+//   sublinear::SparseMatrix   <-> SparseMatrix  (src/matrix/mod.rs:123-372) + trait Matrix (:25-104)
+//   sublinear::NeumannSolver  <-> NeumannSolver (src/solver/neumann.rs:24-93, 469-555) / trait SolverAlgorithm
+//   sublinear::SolverOptions  <-> SolverOptions (src/solver/mod.rs:22-116)
+//   sublinear::SolverResult   <-> SolverResult  (src/solver/mod.rs:121-195)
+//   sublinear::SolverError    <-> SolverError   (src/error.rs:16-138), thrown where Rust returns Err(..)
+// Header only; link against libsublinear_b200.so. The Rust toolchain is not available in the build image, so this is
+// the compiled-language host layer (the Rust shim in ../rust/ is the same mapping, shipped unbuilt).
+#pragma once
+
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+#include "../../include/sublinear_b200.h"
+
+namespace sublinear {
+
+using Precision = double;   // src/types.rs:19
+using IndexType = uint32_t; // src/types.rs:22
+
+enum class ErrorKind : int32_t {
+    MatrixNotDiagonallyDominant = 1, NumericalInstability, ConvergenceFailure, InvalidInput, DimensionMismatch,
+    UnsupportedMatrixFormat, MemoryAllocationError, IndexOutOfBounds, InvalidSparseMatrix, AlgorithmError,
+    WasmBindingError, IoError, SerializationError
+};
+
+class SolverError : public std::runtime_error {
+public:
+    SolverError(int32_t code, std::string msg) : std::runtime_error(std::move(msg)), kind(static_cast<ErrorKind>(code)) {}
+    ErrorKind kind;
+    // fields of ConvergenceFailure / NumericalInstability (src/error.rs:28-47)
+    uint64_t iterations = 0;
+    double residual_norm = 0.0;
+    // SolverError::is_recoverable (src/error.rs:141-152)
+    bool is_recoverable() const {
+        return kind == ErrorKind::ConvergenceFailure || kind == ErrorKind::NumericalInstability ||
+               kind == ErrorKind::MatrixNotDiagonallyDominant;
+    }
+};
+
+namespace detail {
+inline std::string last_error() {
+    char buf[1024];
+    sb200_last_error(buf, sizeof(buf));
+    return buf;
+}
+inline void check(int32_t rc) {
+    if (rc != SB200_OK) throw SolverError(rc, last_error());
+}
+}  // namespace detail
+
+enum class SolveMode : int32_t { Correct = SB200_MODE_CORRECT, RefCompat = SB200_MODE_REF_COMPAT };
+
+struct SolverOptions {
+    Precision tolerance = 1e-6;
+    uint64_t max_iterations = 1000;
+    int32_t convergence_mode = SB200_CONV_RESIDUAL_NORM;
+    int32_t norm_type = SB200_NORM_L2;
+    bool collect_stats = false;
+    uint64_t streaming_interval = 0;
+    std::optional<std::vector<Precision>> initial_guess;
+    bool compute_error_bounds = false;
+    Precision error_bounds_tolerance = 1e-8;
+    bool enable_profiling = false;
+    std::optional<uint64_t> random_seed;
+    SolveMode mode = SolveMode::Correct;
+    int32_t dominance = SB200_DOMINANCE_ROW;
+    int32_t residual_check = SB200_RESIDUAL_EVERY_5;
+
+    static SolverOptions from(const sb200_options &o) {
+        SolverOptions s;
+        s.tolerance = o.tolerance; s.max_iterations = o.max_iterations; s.convergence_mode = o.convergence_mode;
+        s.norm_type = o.norm_type; s.collect_stats = o.collect_stats; s.streaming_interval = o.streaming_interval;
+        s.compute_error_bounds = o.compute_error_bounds; s.error_bounds_tolerance = o.error_bounds_tolerance;
+        s.enable_profiling = o.enable_profiling;
+        return s;
+    }
+    static SolverOptions high_precision() { sb200_options o; sb200_options_high_precision(&o); return from(o); }
+    static SolverOptions fast() { sb200_options o; sb200_options_fast(&o); return from(o); }
+    static SolverOptions streaming(uint64_t interval) { sb200_options o; sb200_options_streaming(&o, interval); return from(o); }
+
+    sb200_options to_c() const {
+        sb200_options o;
+        sb200_options_default(&o);
+        o.tolerance = tolerance; o.max_iterations = max_iterations; o.convergence_mode = convergence_mode;
+        o.norm_type = norm_type; o.collect_stats = collect_stats; o.streaming_interval = streaming_interval;
+        if (initial_guess) { o.initial_guess = initial_guess->data(); o.initial_guess_len = initial_guess->size(); }
+        o.compute_error_bounds = compute_error_bounds; o.error_bounds_tolerance = error_bounds_tolerance;
+        o.enable_profiling = enable_profiling; o.has_random_seed = random_seed.has_value();
+        o.random_seed = random_seed.value_or(0); o.mode = static_cast<int32_t>(mode); o.dominance = dominance;
+        o.residual_check = residual_check;
+        return o;
+    }
+};
+
+struct SolverStats {  // src/types.rs SolverStats: the fields this path fills
+    double total_time_ms = 0.0;
+    uint64_t matvec_count = 0;
+};
+
+struct SolverResult {
+    std::vector<Precision> solution;
+    Precision residual_norm = 0.0;
+    uint64_t iterations = 0;
+    bool converged = false;
+    std::optional<Precision> error_upper_bound;
+    std::optional<SolverStats> stats;
+    uint64_t terms_computed = 0;
+    bool series_converged = false;
+    // SolverResult::meets_quality_criteria (src/solver/mod.rs:192-194)
+    bool meets_quality_criteria(Precision tol) const { return converged && residual_norm <= tol; }
+};
+
+class SparseMatrix {
+public:
+    // SparseMatrix::from_triplets(Vec<(usize,usize,f64)>, rows, cols) (src/matrix/mod.rs:160-199)
+    static SparseMatrix from_triplets(const std::vector<std::tuple<size_t, size_t, Precision>> &t, size_t rows, size_t cols) {
+        std::vector<uint64_t> r(t.size()), c(t.size());
+        std::vector<double> v(t.size());
+        for (size_t i = 0; i < t.size(); i++) { r[i] = std::get<0>(t[i]); c[i] = std::get<1>(t[i]); v[i] = std::get<2>(t[i]); }
+        sb200_matrix *h = nullptr;
+        detail::check(sb200_matrix_from_triplets(r.data(), c.data(), v.data(), t.size(), rows, cols, &h));
+        return SparseMatrix(h);
+    }
+    static SparseMatrix from_csr(const std::vector<uint32_t> &row_ptr, const std::vector<uint32_t> &col_indices,
+                                 const std::vector<Precision> &values, size_t rows, size_t cols) {
+        sb200_matrix *h = nullptr;
+        detail::check(sb200_matrix_from_csr(row_ptr.data(), col_indices.data(), values.data(), rows, cols, values.size(), &h));
+        return SparseMatrix(h);
+    }
+    static SparseMatrix from_dense(const std::vector<Precision> &data, size_t rows, size_t cols) {
+        if (data.size() != rows * cols) throw SolverError(SB200_ERR_DIMENSION_MISMATCH, "dense_to_sparse_conversion");
+        sb200_matrix *h = nullptr;
+        detail::check(sb200_matrix_from_dense(data.data(), rows, cols, &h));
+        return SparseMatrix(h);
+    }
+    static SparseMatrix identity(size_t n) { sb200_matrix *h = nullptr; detail::check(sb200_matrix_identity(n, &h)); return SparseMatrix(h); }
+    static SparseMatrix diagonal(const std::vector<Precision> &d) {
+        sb200_matrix *h = nullptr;
+        detail::check(sb200_matrix_diagonal(d.data(), d.size(), &h));
+        return SparseMatrix(h);
+    }
+    SparseMatrix(SparseMatrix &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    SparseMatrix &operator=(SparseMatrix &&o) noexcept { if (this != &o) { sb200_matrix_free(h_); h_ = o.h_; o.h_ = nullptr; } return *this; }
+    SparseMatrix(const SparseMatrix &) = delete;
+    SparseMatrix &operator=(const SparseMatrix &) = delete;
+    ~SparseMatrix() { sb200_matrix_free(h_); }
+
+    // trait Matrix (src/matrix/mod.rs:25-104)
+    size_t rows() const { uint64_t v; detail::check(sb200_matrix_rows(h_, &v)); return v; }
+    size_t cols() const { uint64_t v; detail::check(sb200_matrix_cols(h_, &v)); return v; }
+    size_t nnz() const { uint64_t v; detail::check(sb200_matrix_nnz(h_, &v)); return v; }
+    bool is_square() const { return rows() == cols(); }
+    std::optional<Precision> get(size_t row, size_t col) const {
+        double v; int32_t p;
+        detail::check(sb200_matrix_get(h_, row, col, &v, &p));
+        return p ? std::optional<Precision>(v) : std::nullopt;
+    }
+    bool is_diagonally_dominant() const { int32_t o; detail::check(sb200_matrix_is_diagonally_dominant(h_, SB200_DOMINANCE_ROW, &o)); return o; }
+    std::optional<Precision> diagonal_dominance_factor() const {
+        double f; int32_t p;
+        detail::check(sb200_matrix_diagonal_dominance_factor(h_, &f, &p));
+        return p ? std::optional<Precision>(f) : std::nullopt;
+    }
+    void multiply_vector(const std::vector<Precision> &x, std::vector<Precision> &result) const {
+        detail::check(sb200_matrix_multiply_vector(h_, x.data(), x.size(), result.data(), result.size()));
+    }
+    void multiply_vector_add(const std::vector<Precision> &x, std::vector<Precision> &result) const {
+        detail::check(sb200_matrix_multiply_vector_add(h_, x.data(), x.size(), result.data(), result.size()));
+    }
+    void scale(Precision factor) { detail::check(sb200_matrix_scale(h_, factor)); }
+    const char *format_name() const { return "CSR"; }
+    const sb200_matrix *handle() const { return h_; }
+
+private:
+    explicit SparseMatrix(sb200_matrix *h) : h_(h) {}
+    sb200_matrix *h_ = nullptr;
+};
+
+class NeumannSolver {
+public:
+    NeumannSolver(size_t max_terms, Precision series_tolerance) { detail::check(sb200_neumann_new(max_terms, series_tolerance, &h_)); }
+    static NeumannSolver default_() { sb200_solver *h; detail::check(sb200_neumann_default(&h)); return NeumannSolver(h); }
+    static NeumannSolver high_precision() { sb200_solver *h; detail::check(sb200_neumann_high_precision(&h)); return NeumannSolver(h); }
+    static NeumannSolver fast() { sb200_solver *h; detail::check(sb200_neumann_fast(&h)); return NeumannSolver(h); }
+    NeumannSolver(NeumannSolver &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    NeumannSolver(const NeumannSolver &) = delete;
+    ~NeumannSolver() { sb200_solver_free(h_); }
+    NeumannSolver &with_adaptive_truncation(bool e) { detail::check(sb200_neumann_with_adaptive_truncation(h_, e)); return *this; }
+    NeumannSolver &with_power_caching(bool e) { detail::check(sb200_neumann_with_power_caching(h_, e)); return *this; }
+    const char *algorithm_name() const { return sb200_solver_algorithm_name(h_); }
+
+    // SolverAlgorithm::solve(&self, matrix, b, options) -> Result<SolverResult> (src/solver/neumann.rs:469-555)
+    SolverResult solve(const SparseMatrix &matrix, const std::vector<Precision> &b, const SolverOptions &options = {}) const {
+        sb200_options o = options.to_c();
+        sb200_result r;
+        SolverResult out;
+        out.solution.resize(b.size());
+        const int32_t rc = sb200_solve_into(h_, matrix.handle(), b.data(), b.size(), &o, out.solution.data(), &r);
+        out.residual_norm = r.residual_norm; out.iterations = r.iterations; out.converged = r.converged;
+        out.terms_computed = r.terms_computed; out.series_converged = r.series_converged;
+        if (r.has_error_bounds) out.error_upper_bound = r.error_upper_bound;
+        if (r.has_stats) out.stats = SolverStats{r.total_time_ms, r.matvec_count};
+        if (rc != SB200_OK) {
+            SolverError e(rc, detail::last_error());
+            e.iterations = r.iterations;
+            e.residual_norm = r.residual_norm;
+            throw e;
+        }
+        return out;
+    }
+
+private:
+    explicit NeumannSolver(sb200_solver *h) : h_(h) {}
+    sb200_solver *h_ = nullptr;
+};
+
+}  // namespace sublinear

@@ -151,7 +151,7 @@ struct SetupOut {
     double *min_factor_bits;       // optional: min diag/off ratio (as double, atomicMin on ordered bits)
 };
 int32_t launch_setup_rows(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
-                          int compat_diag, SetupOut out, cudaStream_t stream);
+                          uint32_t row_base, int compat_diag, SetupOut out, cudaStream_t stream);
 int32_t launch_col_dominance(const double *col_diag, const double *col_off, uint32_t n, unsigned long long *first_bad,
                              cudaStream_t stream);
 // iteration 0 (neumann.rs:191-211 + first compute_next_term): c = b*dinv; t = c (or (b - Ax0)*dinv); x = base + t

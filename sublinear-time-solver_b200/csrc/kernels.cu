@@ -32,8 +32,8 @@ const TileCfg kTileCfgs[kNumTileCfgs] = {{256, 128, 1536}, {512, 256, 2816}, {25
 int default_tile_cfg() {
     static int cfg = [] {
         const char *e = getenv("SUBLINEAR_B200_TILE_CFG");
-        int v = e ? atoi(e) : 0;
-        return (v >= 0 && v < kNumTileCfgs) ? v : 0;
+        int v = e ? atoi(e) : -1;  // -1 = warp-stream kernel (default); 0.. = TMA-staged tile pipeline variants
+        return (v >= -1 && v < kNumTileCfgs) ? v : -1;
     }();
     return cfg;
 }
@@ -586,7 +586,10 @@ static int32_t launch_any(int cfg, Epilogue epi, const TileKernelArgs &a, cudaSt
     }
 }
 
+static int32_t launch_warp_any(Epilogue epi, const TileKernelArgs &a, cudaStream_t stream, int *mg);
+
 int32_t launch_tile_kernel(int cfg, Epilogue epi, const TileKernelArgs &a, cudaStream_t stream) {
+    if (cfg < 0) return launch_warp_any(epi, a, stream, nullptr);
     if (reinterpret_cast<uintptr_t>(a.xin) & 15u)  // 16-byte gathers and the TMA window copy
         return fail(SB200_ERR_INVALID_INPUT, "device vectors must be 16-byte aligned");
     return launch_any(cfg, epi, a, stream, nullptr);
@@ -595,8 +598,172 @@ int32_t launch_tile_kernel(int cfg, Epilogue epi, const TileKernelArgs &a, cudaS
 int tile_kernel_max_grid(int cfg, Epilogue epi) {
     int mg = 0;
     TileKernelArgs dummy{};
-    if (launch_any(cfg, epi, dummy, nullptr, &mg) != SB200_OK) return 0;
+    if ((cfg < 0 ? launch_warp_any(epi, dummy, nullptr, &mg) : launch_any(cfg, epi, dummy, nullptr, &mg)) != SB200_OK) return 0;
     return mg;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the warp-stream kernel (tile configuration -1)
+// ---------------------------------------------------------------------------------------------------------
+// Same three epilogues as the tile kernel, no CTA-level synchronisation at all: every warp owns blocks of 32
+// consecutive rows.  The block's contiguous slice of col_indices / values is read with coalesced 128-bit loads
+// (4 elements per lane) straight into registers, the x[col] gathers go to registers as well, and only the products
+// pass through a 1 KB warp-private shared-memory chunk so that lane r can add the products of row r LEFT TO RIGHT
+// (the reference's order, bit for bit) — 4-5 LSU operations per non-zero instead of the 7 of the staged pipeline,
+// which matters because the load/store pipe, not HBM, is what this access pattern saturates.
+// Lane r <-> row r also makes every epilogue load/store fully coalesced.
+template <int EPI, int NT>
+__global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
+    constexpr int WARPS = NT / 32;
+    constexpr uint32_t CH = 128;         // elements per chunk: 4 per lane
+    constexpr uint32_t kLongRow = 1024;  // a block holding a longer row falls back to warp-per-row sums
+    __shared__ __align__(16) double s_prod[WARPS][CH];
+    __shared__ double s_red[WARPS];
+    __shared__ int s_flag;
+
+    if (EPI != EPI_SPMV) {
+        if (!a.force && a.ctl->alive == 0) return;  // loop already finished: no-op launch
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t pol_stream = policy_evict_first();
+    const uint64_t pol_gather = policy_evict_last();
+    const uint32_t nrows = a.nrows;
+    const uint32_t nblocks = (nrows + 31u) >> 5;
+    const uint32_t nwarps = gridDim.x * WARPS;
+    double *__restrict__ sp = s_prod[warp];
+
+    double sq = 0.0, aux = 0.0;
+    for (uint32_t blk = blockIdx.x * WARPS + warp; blk < nblocks; blk += nwarps) {
+        const uint32_t row_first = blk << 5;
+        const uint32_t row = row_first + lane;
+        const bool active = row < nrows;
+        const uint32_t rlast = min(nrows, row_first + 32u) - 1u;  // last row of the block
+        const uint32_t rs = a.row_ptr[active ? row : rlast + 1u];
+        const uint32_t re = active ? a.row_ptr[row + 1u] : rs;
+        const uint32_t b0 = __shfl_sync(0xffffffffu, rs, 0);
+        const uint32_t b1 = __shfl_sync(0xffffffffu, re, (int)(rlast & 31u));
+        double own = 0.0, dv = 0.0, xs = 0.0, rh = 0.0;
+        if (active) {
+            if (EPI == EPI_PUSH) {
+                own = a.xin[a.row_base + row];
+                dv = a.dinv[row];
+                xs = a.sol[row];
+            } else if (EPI == EPI_RESID) {
+                rh = a.rhs[row];
+            } else if (a.accumulate) {
+                xs = a.out[row];
+            }
+        }
+        double acc = (EPI == EPI_SPMV && a.accumulate) ? xs : 0.0;
+        const uint32_t max_len = __reduce_max_sync(0xffffffffu, re - rs);
+        if (max_len <= kLongRow) {
+            for (uint32_t c0 = b0 & ~3u; c0 < b1; c0 += CH) {
+                const uint32_t e = c0 + 4u * lane;  // this lane's elements e .. e+3 (16-byte aligned slices)
+                double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+                if (e < b1) {
+                    uint32_t cx, cy, cz, cw;
+                    double v0, v1, v2, v3;
+                    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                                 : "=r"(cx), "=r"(cy), "=r"(cz), "=r"(cw)
+                                 : "l"(a.cols + e), "l"(pol_stream));
+                    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                                 : "=d"(v0), "=d"(v1)
+                                 : "l"(a.vals + e), "l"(pol_stream));
+                    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                                 : "=d"(v2), "=d"(v3)
+                                 : "l"(a.vals + e + 2), "l"(pol_stream));
+                    // elements outside [b0,b1) belong to neighbouring rows or to the zero padding: their columns are
+                    // valid, their products are never summed
+                    const double x0 = ld_gather(a.xin + cx, pol_gather);
+                    const double x1 = ld_gather(a.xin + cy, pol_gather);
+                    const double x2 = ld_gather(a.xin + cz, pol_gather);
+                    const double x3 = ld_gather(a.xin + cw, pol_gather);
+                    p0 = v0 * x0;
+                    p1 = v1 * x1;
+                    p2 = v2 * x2;
+                    p3 = v3 * x3;
+                }
+                *reinterpret_cast<double2 *>(sp + 4 * lane) = make_double2(p0, p1);
+                *reinterpret_cast<double2 *>(sp + 4 * lane + 2) = make_double2(p2, p3);
+                __syncwarp();
+                // left-to-right accumulation, the order of CSRStorage::multiply_vector_add (sparse.rs:193-203)
+                const uint32_t lo = max(rs, c0), hi = min(re, c0 + CH);
+                for (uint32_t k = lo; k < hi; k++) acc += sp[k - c0];
+                __syncwarp();
+            }
+        } else {
+            // a block holding a very long row: one row at a time, lane-strided partial sums + shuffle tree
+            // (order differs from the reference: tolerance-level parity only)
+            const uint32_t nr = rlast - row_first + 1u;
+            for (uint32_t i = 0; i < nr; i++) {
+                const uint32_t s = __shfl_sync(0xffffffffu, rs, (int)i), t = __shfl_sync(0xffffffffu, re, (int)i);
+                double part = 0.0;
+                for (uint32_t k = s + lane; k < t; k += 32u)
+                    part += ld_stream_f64(a.vals + k) * ld_gather(a.xin + ld_stream_u32(a.cols + k), pol_gather);
+                part = warp_sum(part);
+                if ((uint32_t)lane == i) acc += part;
+            }
+        }
+        if (active) {
+            if (EPI == EPI_SPMV) {
+                a.out[row] = acc;
+            } else if (EPI == EPI_PUSH) {
+                const double tmp = acc * dv;   // temp *= d_inv        (neumann.rs:289-291)
+                const double tn = own - tmp;   // term -= temp         (neumann.rs:294-296)
+                a.out[row] = tn;
+                a.sol[row] = xs + tn;          // solution += term     (neumann.rs:264-266)
+                sq += tn * tn;                 // l2_norm accumulation (solver/mod.rs:369-371)
+                if (a.identity_res) {
+                    const double r = tn / dv;  // (D o t')_i = (b - A x)_i, SURVEY F12
+                    aux += r * r;
+                }
+            } else {
+                const double r = acc - rh;     // r = A x - rhs        (neumann.rs:308-310)
+                sq += r * r;
+            }
+        }
+    }
+    if (EPI != EPI_SPMV) {
+        grid_reduce_and_tail<NT>(sq, aux, a.ctl, a.partials, EPI == EPI_PUSH ? TAIL_TERM : TAIL_RESID, a.it,
+                                 a.last_in_iter, a.identity_res, a.defer_tail, a.norm_log, s_red, &s_flag);
+    }
+}
+
+template <int EPI, int NT>
+static int32_t launch_warp_one(const TileKernelArgs &a, cudaStream_t stream, int *max_grid_out) {
+    static int max_grid[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) return fail(SB200_ERR_ALGORITHM, "device index %d out of range", dev);
+    if (max_grid[dev] == 0) {
+        int per_sm = 0, sms = 0;
+        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, warp_kernel<EPI, NT>, NT, 0));
+        SB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (per_sm < 1) return fail(SB200_ERR_ALGORITHM, "warp kernel does not fit on an SM");
+        static int cap = [] { const char *e = getenv("SUBLINEAR_B200_WARP_CTAS"); return e ? atoi(e) : 0; }();
+        if (cap > 0 && per_sm > cap) per_sm = cap;
+        max_grid[dev] = per_sm * sms;  // persistent grid: a whole number of CTAs per SM (148 SMs on B200)
+    }
+    if (max_grid_out) {
+        *max_grid_out = max_grid[dev];
+        return SB200_OK;
+    }
+    if (a.nrows == 0 && EPI == EPI_SPMV) return SB200_OK;
+    const uint32_t nblocks = (a.nrows + 31u) / 32u;
+    unsigned need = (nblocks + NT / 32 - 1) / (NT / 32);
+    unsigned grid = need < (unsigned)max_grid[dev] ? need : (unsigned)max_grid[dev];
+    if (grid == 0) grid = 1;
+    warp_kernel<EPI, NT><<<grid, NT, 0, stream>>>(a);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+static int32_t launch_warp_any(Epilogue epi, const TileKernelArgs &a, cudaStream_t stream, int *mg) {
+    switch (epi) {
+        case EPI_SPMV: return launch_warp_one<EPI_SPMV, 256>(a, stream, mg);
+        case EPI_PUSH: return launch_warp_one<EPI_PUSH, 256>(a, stream, mg);
+        default: return launch_warp_one<EPI_RESID, 256>(a, stream, mg);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -605,9 +772,11 @@ int tile_kernel_max_grid(int cfg, Epilogue epi) {
 __device__ __forceinline__ void atomic_min_u64(unsigned long long *addr, unsigned long long v) { atomicMin(addr, v); }
 
 __global__ void setup_rows_kernel(const double *__restrict__ vals, const uint32_t *__restrict__ cols,
-                                  const uint32_t *__restrict__ row_ptr, uint32_t nrows, int compat_diag, SetupOut o) {
-    for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += gridDim.x * blockDim.x) {
-        const uint32_t rs = row_ptr[row], re = row_ptr[row + 1];
+                                  const uint32_t *__restrict__ row_ptr, uint32_t nrows, uint32_t row_base, int compat_diag,
+                                  SetupOut o) {
+    for (uint32_t lrow = blockIdx.x * blockDim.x + threadIdx.x; lrow < nrows; lrow += gridDim.x * blockDim.x) {
+        const uint32_t rs = row_ptr[lrow], re = row_ptr[lrow + 1];
+        const uint32_t row = row_base + lrow;  // global index of this row = column of its diagonal entry
         double diag_last = 0.0, diag_sum = 0.0, off = 0.0;
         bool has = false;
         for (uint32_t k = rs; k < re; k++) {
@@ -623,7 +792,7 @@ __global__ void setup_rows_kernel(const double *__restrict__ vals, const uint32_
             }
         }
         if (o.col_diag && has) o.col_diag[row] = diag_last;
-        if (diag_last < off) atomic_min_u64(o.first_bad_dd, row);  // mod.rs:480
+        if (diag_last < off) atomic_min_u64(o.first_bad_dd, lrow);  // mod.rs:480
         double d = diag_sum;
         if (compat_diag && has) {
             // CSRStorage::get (sparse.rs:142-155): bisection over the (column-sorted) row; with duplicated
@@ -643,10 +812,10 @@ __global__ void setup_rows_kernel(const double *__restrict__ vals, const uint32_
             if (!found) has = false;  // unsorted row: the reference's binary search would miss it too
         }
         if (!has || fabs(d) < 1e-14) {  // neumann.rs:174-187
-            atomic_min_u64(o.first_bad_diag, row);
-            o.dinv[row] = 0.0;
+            atomic_min_u64(o.first_bad_diag, lrow);
+            o.dinv[lrow] = 0.0;
         } else {
-            o.dinv[row] = 1.0 / d;
+            o.dinv[lrow] = 1.0 / d;
         }
         if (o.min_factor_bits && off > 0.0) {
             // positive doubles order like their bit patterns
@@ -657,11 +826,11 @@ __global__ void setup_rows_kernel(const double *__restrict__ vals, const uint32_
 }
 
 int32_t launch_setup_rows(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
-                          int compat_diag, SetupOut out, cudaStream_t stream) {
+                          uint32_t row_base, int compat_diag, SetupOut out, cudaStream_t stream) {
     if (nrows == 0) return SB200_OK;
     unsigned grid = (nrows + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;
-    setup_rows_kernel<<<grid, 256, 0, stream>>>(vals, cols, row_ptr, nrows, compat_diag, out);
+    setup_rows_kernel<<<grid, 256, 0, stream>>>(vals, cols, row_ptr, nrows, row_base, compat_diag, out);
     SB_CUDA(cudaGetLastError());
     return SB200_OK;
 }

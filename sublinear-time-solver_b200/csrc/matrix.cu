@@ -144,7 +144,7 @@ int32_t matrix_from_host_csr(const uint64_t *row_ptr64, const uint32_t *row_ptr3
     SB_TRY(require_device(m->device));  // after host-side validation: input errors do not need a GPU to be reported
     m->tile_cfg = default_tile_cfg();
     std::vector<TileDesc> tiles;
-    build_tiles(rp, nrows, kTileCfgs[m->tile_cfg], tiles);
+    build_tiles(rp, nrows, kTileCfgs[m->tile_cfg < 0 ? 0 : m->tile_cfg], tiles);  // unused by the warp-stream kernel
     m->ntiles = (uint32_t)(tiles.size() - 1);
 
     // device arrays are padded so that the 16-byte-granular bulk copies may over-read past nnz
@@ -211,8 +211,8 @@ int32_t matrix_analyse(sb200_matrix *m, int mode, bool need_cols) {
         o.col_diag = col_diag.p;
         o.col_off = col_off.p;
     }
-    SB_TRY(launch_setup_rows(m->d_vals.p, m->d_cols.p, m->d_row_ptr.p, (uint32_t)n, mode == SB200_MODE_REF_COMPAT, o,
-                             m->stream));
+    SB_TRY(launch_setup_rows(m->d_vals.p, m->d_cols.p, m->d_row_ptr.p, (uint32_t)n, (uint32_t)m->row_base,
+                             mode == SB200_MODE_REF_COMPAT, o, m->stream));
     if (need_cols) SB_TRY(launch_col_dominance(col_diag.p, col_off.p, (uint32_t)m->ncols, scal.p + 2, m->stream));
     unsigned long long res[4];
     SB_CUDA(cudaMemcpyAsync(res, scal.p, sizeof(res), cudaMemcpyDeviceToHost, m->stream));

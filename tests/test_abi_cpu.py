@@ -128,3 +128,25 @@ def test_product_never_touches_the_oracle():
                 assert "/root/reference" not in txt, f
     out = subprocess.run(["ldd", sb.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def _build_cpp_unit_tests(tmp_path):
+    exe = os.path.join(str(tmp_path), "test_reference_units")
+    src = os.path.join(os.path.dirname(__file__), "cpp", "test_reference_units.cpp")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-o", exe, src, "-L", sb.PKG_DIR, "-lsublinear_b200",
+                        f"-Wl,-rpath,{sb.PKG_DIR}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return exe
+
+
+def test_cpp_mirror_of_reference_api_compiles_and_links(tmp_path):
+    """cpp/sublinear.hpp (SparseMatrix / NeumannSolver / SolverOptions / SolverResult / SolverError over the C ABI)
+    compiles with plain g++ and links against the library; the program is RUN by the gpu test below."""
+    _build_cpp_unit_tests(tmp_path)
+
+
+@pytest.mark.gpu
+def test_cpp_reference_unit_tests_run(tmp_path):
+    exe = _build_cpp_unit_tests(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "all passed" in r.stdout, r.stdout + r.stderr
