@@ -104,7 +104,22 @@ struct LoopCtl {
     uint32_t terms;      // terms_computed
     uint32_t iterations;
     uint32_t ticket;     // last-CTA election
-    uint32_t pad[2];
+    uint32_t xchg;       // row-partitioned P2P runs: number of exchanges consumed so far (drives epoch + slot parity)
+    uint32_t peer_timeout;  // a peer never signalled (the loop is stopped and reported as AlgorithmError)
+};
+
+// Row-partitioned runs over peer memory (csrc/dist.cu): every rank maps every other rank's exchange arena (CUDA IPC);
+// a kernel stores its slice of the new term (and, when a residual check follows, of the solution) straight into all
+// peers' buffers over NVLink, its last CTA publishes the rank's partial sums + a flag to all peers, and a one-warp
+// wait kernel sums the partials in rank order (bitwise identical on every rank) and takes the loop decision.
+constexpr int kMaxPeers = 8;
+struct PeerExchange {               // all zero = not used (single GPU, or the NCCL path)
+    int world, rank;
+    unsigned long long epoch_base;  // exchange e of this solve signals epoch_base + e
+    double *t_out[kMaxPeers];       // peer p's term buffer being written this launch (global row indexing)
+    double *x_out[kMaxPeers];       // peer p's full-length solution mirror, or null when x is not published
+    double *slots[kMaxPeers];       // peer p's partial-sum slots [2 parities][world][2]
+    unsigned long long *flags[kMaxPeers];  // peer p's flag array [world]
 };
 
 enum Epilogue { EPI_SPMV = 0, EPI_PUSH = 1, EPI_RESID = 2 };
@@ -137,6 +152,7 @@ struct TileKernelArgs {
     int defer_tail;       // distributed: only publish the local sums; a later kernel runs the loop logic
     double *norm_log;     // optional: norm_log[it] = ||t_it||^2 (bare recurrence)
     unsigned long long *phase_log;  // debug ($SUBLINEAR_B200_PHASE_LOG=1): per-phase cycles of thread 0, summed over CTAs
+    PeerExchange px;      // row-partitioned P2P exchange (warp-stream kernel only)
 };
 
 // launchers (kernels.cu). grid = 0 -> persistent grid sized from occupancy.
@@ -170,6 +186,8 @@ struct InitArgs {
     int defer_tail;
     int skip_term0;        // max_terms == 0 / max_iterations == 0: x = base, no term accumulated
     double *norm_log;
+    uint32_t row_base;     // global index of local row 0 (P2P publishing)
+    PeerExchange px;
 };
 int32_t launch_init_state(const InitArgs &a, cudaStream_t stream);
 int init_state_grid();
@@ -177,5 +195,12 @@ int32_t launch_scale(double *v, uint64_t n, double factor, cudaStream_t stream);
 // distributed: finish the loop logic after the partial norms were all-reduced (kind: 1 = term, 2 = residual)
 int32_t launch_dist_tail(LoopCtl *ctl, int kind, uint32_t it, int last_in_iter, int identity_res, int force,
                          double *norm_log, cudaStream_t stream);
+// P2P exchange: wait for all ranks' flags of the current exchange, sum their partials, run the loop logic
+int32_t launch_peer_wait(LoopCtl *ctl, const unsigned long long *flags_local, const double *slots_local, int world,
+                         unsigned long long epoch_base, int kind, uint32_t it, int last_in_iter, int identity_res,
+                         int force, double *norm_log, cudaStream_t stream);
+// P2P exchange: copy this rank's slice src[0..n) to dst[p] + offset on every rank, then signal (kind 0: no sums)
+int32_t launch_peer_publish(const double *src, uint64_t n, uint64_t offset, double *const *dst, LoopCtl *ctl,
+                            const PeerExchange &px, int force, cudaStream_t stream);
 
 }  // namespace sb200

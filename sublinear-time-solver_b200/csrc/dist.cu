@@ -76,10 +76,28 @@ int32_t load_nccl() {
 
 }  // namespace
 
+// Exchange arena: one cudaMalloc block per rank, mapped by every other rank through CUDA IPC.
+//   [0, 256)        flags  : world x u64, flags[r] = last epoch signalled by rank r
+//   [256, 1024)     slots  : [2 parities][world][2] doubles, partial sums of the current exchange
+//   [1024, ...)     T0 | T1 | X : three full-length vectors (cap doubles each): term ping-pong + solution mirror
+struct PeerArena {
+    void *base = nullptr;
+    uint64_t cap = 0;  // doubles per vector
+    void *peer[kMaxPeers] = {nullptr};
+    unsigned long long *flags(int p) const { return reinterpret_cast<unsigned long long *>(peer[p]); }
+    double *slots(int p) const { return reinterpret_cast<double *>(static_cast<char *>(peer[p]) + 256); }
+    double *vec(int p, int which) const {
+        return reinterpret_cast<double *>(static_cast<char *>(peer[p]) + 1024) + (size_t)which * cap;
+    }
+};
+
 struct sb200_comm {
     int rank = 0, world = 1, device = 0;
     ncclComm_t comm = nullptr;
     cudaStream_t stream = nullptr;
+    bool p2p = false;  // exchange over IPC-mapped peer memory (default when world <= 8); else NCCL collectives
+    PeerArena arena;
+    unsigned long long epoch_base = 0;
 };
 
 namespace {
@@ -126,6 +144,126 @@ int32_t agree_status(sb200_comm *c, int32_t local, Workspace &ws, cudaStream_t s
     return (int32_t)v;
 }
 
+
+// (Re)allocate the exchange arena for vectors of `nfull` doubles and map every peer's. Collective.
+int32_t ensure_arena(sb200_comm *c, uint64_t nfull) {
+    PeerArena &A = c->arena;
+    if (A.cap >= nfull && A.base) return SB200_OK;
+    cudaStream_t st = c->stream;
+    DevBuf<double> bar;
+    SB_TRY(bar.alloc(1));
+    if (A.base) {  // growth: unmap peers, make sure everybody did, then free
+        for (int p = 0; p < c->world; p++)
+            if (p != c->rank && A.peer[p]) cudaIpcCloseMemHandle(A.peer[p]);
+        SB_NCCL(g_nccl.AllReduce(bar.p, bar.p, 1, ncclDouble, ncclSum, c->comm, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        cudaFree(A.base);
+        A.base = nullptr;
+        A.cap = 0;
+    }
+    const uint64_t cap = (nfull + 31) & ~31ull;
+    const size_t bytes = 1024 + (size_t)3 * cap * sizeof(double);
+    cudaError_t e = cudaMalloc(&A.base, bytes);
+    if (e != cudaSuccess) {
+        A.base = nullptr;
+        return fail(SB200_ERR_MEMORY_ALLOCATION, "cudaMalloc of the %zu-byte exchange arena failed: %s", bytes, cudaGetErrorString(e));
+    }
+    SB_CUDA(cudaMemset(A.base, 0, bytes));
+    SB_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t mine;
+    SB_CUDA(cudaIpcGetMemHandle(&mine, A.base));
+    DevBuf<char> hb;
+    SB_TRY(hb.alloc((size_t)c->world * sizeof(cudaIpcMemHandle_t)));
+    SB_CUDA(cudaMemcpyAsync(hb.p + (size_t)c->rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, st));
+    SB_NCCL(g_nccl.AllGather(hb.p + (size_t)c->rank * sizeof(mine), hb.p, sizeof(mine), ncclChar, c->comm, st));
+    std::vector<cudaIpcMemHandle_t> all(c->world);
+    SB_CUDA(cudaMemcpyAsync(all.data(), hb.p, (size_t)c->world * sizeof(mine), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    for (int p = 0; p < c->world; p++) {
+        if (p == c->rank) {
+            A.peer[p] = A.base;
+            continue;
+        }
+        e = cudaIpcOpenMemHandle(&A.peer[p], all[p], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(SB200_ERR_ALGORITHM, "cudaIpcOpenMemHandle for rank %d failed: %s (set SUBLINEAR_B200_DIST=nccl)", p,
+                        cudaGetErrorString(e));
+        }
+    }
+    A.cap = cap;
+    return SB200_OK;
+}
+
+PeerExchange make_px(const sb200_comm *c, int t_which, bool publish_x) {
+    PeerExchange px{};
+    px.world = c->world;
+    px.rank = c->rank;
+    px.epoch_base = c->epoch_base;
+    for (int p = 0; p < c->world; p++) {
+        px.t_out[p] = t_which >= 0 ? c->arena.vec(p, t_which) : nullptr;
+        px.x_out[p] = publish_x ? c->arena.vec(p, 2) : nullptr;
+        px.slots[p] = c->arena.slots(p);
+        px.flags[p] = c->arena.flags(p);
+    }
+    return px;
+}
+
+int32_t peer_wait(sb200_comm *c, LoopCtl *ctl, int kind, uint64_t it, int last, int identity, int force, double *norm_log,
+                  cudaStream_t st) {
+    return launch_peer_wait(ctl, c->arena.flags(c->rank), c->arena.slots(c->rank), c->world, c->epoch_base, kind,
+                            (uint32_t)it, last, identity, force, norm_log, st);
+}
+
+// The P2P flavour of sb200_dist_push_iterations_dev / sb200_dist_solve: same control flow as the NCCL flavour below,
+// the exchange is fused into the kernels (see PeerExchange in common.hpp).
+int32_t push_iterations_p2p(sb200_comm *c, sb200_matrix *mm, const DistPlan &p, Workspace &ws, const double *b_local_dev,
+                            uint64_t nterms, double *x, cudaStream_t st) {
+    SB_TRY(ensure_arena(c, p.per * c->world));
+    c->epoch_base += 1ull << 24;  // a fresh epoch range per call: flags left by earlier calls can never satisfy a wait
+    const int cfg = -1;
+    LoopCtl h{};
+    h.res_norm = INFINITY;
+    h.alive = 1;
+    h.max_terms = h.max_iterations = 0xFFFFFFFFu;
+    *ws.h_ctl = h;
+    SB_CUDA(cudaMemcpyAsync(ws.ctl.p, ws.h_ctl, sizeof(LoopCtl), cudaMemcpyHostToDevice, st));
+    InitArgs ia{};
+    ia.b = b_local_dev;
+    ia.dinv = mm->d_dinv[0].p;
+    ia.t_out = c->arena.vec(c->rank, 0) + p.row0;
+    ia.x_out = x;
+    ia.n = (uint32_t)p.nloc;
+    ia.ctl = ws.ctl.p;
+    ia.partials = ws.partials.p;
+    ia.row_base = (uint32_t)p.row0;
+    ia.px = make_px(c, 0, false);
+    SB_TRY(launch_init_state(ia, st));
+    SB_TRY(peer_wait(c, ws.ctl.p, 1, 0, 0, 0, 1, ws.norm_log.p, st));
+    TileKernelArgs base{};
+    fill_tile_args(mm, base);
+    base.ctl = ws.ctl.p;
+    base.partials = ws.partials.p;
+    base.force = 1;
+    base.sol = x;
+    base.dinv = mm->d_dinv[0].p;
+    SB_CUDA(cudaEventRecord(ws.ev0, st));
+    for (uint64_t it = 1; it <= nterms; it++) {
+        TileKernelArgs a = base;
+        a.xin = c->arena.vec(c->rank, (int)((it - 1) & 1));
+        a.xin_own = a.xin + p.row0;
+        a.out = c->arena.vec(c->rank, (int)(it & 1)) + p.row0;
+        a.it = (uint32_t)it;
+        a.px = make_px(c, (int)(it & 1), false);
+        if (getenv("SUBLINEAR_B200_DEBUG_NOSTORE"))  // timing aid: compute + signalling only, no remote term stores
+            for (int q = 0; q < c->world; q++) a.px.t_out[q] = nullptr;
+        SB_TRY(launch_tile_kernel(cfg, EPI_PUSH, a, st));
+        SB_TRY(peer_wait(c, ws.ctl.p, 1, it, 0, 0, 1, ws.norm_log.p, st));
+    }
+    SB_CUDA(cudaEventRecord(ws.ev1, st));
+    return SB200_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -157,6 +295,8 @@ int32_t sb200_comm_init(int32_t rank, int32_t world, const uint8_t id[SB200_UNIQ
     memcpy(&u, id, sizeof(u));
     SB_NCCL(g_nccl.CommInitRank(&c->comm, world, u, rank));
     SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const char *mode = getenv("SUBLINEAR_B200_DIST");  // "nccl" forces the collective-based exchange
+    c->p2p = world > 1 && world <= kMaxPeers && !(mode && std::string(mode) == "nccl");
     *out = c.release();
     return SB200_OK;
 }
@@ -164,6 +304,9 @@ int32_t sb200_comm_init(int32_t rank, int32_t world, const uint8_t id[SB200_UNIQ
 void sb200_comm_free(sb200_comm *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (int p = 0; p < c->world; p++)
+        if (p != c->rank && c->arena.peer[p]) cudaIpcCloseMemHandle(c->arena.peer[p]);
+    if (c->arena.base) cudaFree(c->arena.base);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     delete c;
@@ -193,6 +336,7 @@ int32_t sb200_dist_matrix_from_csr(sb200_comm *c, uint64_t n_global, uint64_t ro
     const uint64_t nloc = row1 - row0;
     SB_TRY(matrix_from_host_csr(row_ptr, nullptr, col_indices, values, nloc, n_global, row_ptr[nloc], true, out));
     (*out)->distributed = true;
+    (*out)->tile_cfg = -1;  // the fused exchange lives in the warp-stream kernel
     (*out)->row_base = row0;
     (*out)->n_global = n_global;
     return SB200_OK;
@@ -221,13 +365,23 @@ int32_t sb200_dist_push_iterations_dev(sb200_comm *c, const sb200_matrix *m, con
     const int32_t rc = agree_status(c, local_rc, *ws, st);
     if (rc != SB200_OK) return local_rc != SB200_OK ? local_rc : fail(rc, "another rank rejected its row block");
 
+    double *x = x_local_dev ? x_local_dev : ws->x.p;
+    if (c->p2p) {
+        SB_TRY(push_iterations_p2p(c, mm, p, *ws, b_local_dev, nterms, x, st));
+        std::vector<double> plog(nterms + 1);
+        SB_CUDA(cudaMemcpyAsync(plog.data(), ws->norm_log.p, (nterms + 1) * 8, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        if (elapsed_ms) SB_CUDA(cudaEventElapsedTime(elapsed_ms, ws->ev0, ws->ev1));
+        if (term_norms)
+            for (uint64_t k = 0; k < nterms; k++) term_norms[k] = std::sqrt(plog[k + 1]);
+        return SB200_OK;
+    }
     LoopCtl h{};
     h.res_norm = INFINITY;
     h.alive = 1;
     h.max_terms = h.max_iterations = 0xFFFFFFFFu;
     *ws->h_ctl = h;
     SB_CUDA(cudaMemcpyAsync(ws->ctl.p, ws->h_ctl, sizeof(LoopCtl), cudaMemcpyHostToDevice, st));
-    double *x = x_local_dev ? x_local_dev : ws->x.p;
     InitArgs ia{};
     ia.b = b_local_dev;
     ia.dinv = m->d_dinv[0].p;
@@ -292,6 +446,7 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
     const bool compat = opt->mode == SB200_MODE_REF_COMPAT;
     const bool identity = opt->residual_check == SB200_RESIDUAL_IDENTITY;
     const bool multi = c->world > 1;
+    const bool p2p = multi && c->p2p;
     const uint64_t max_it = opt->max_iterations, max_terms = s->max_terms;
     if (max_it >= 0xFFFFFFFFull || max_terms >= 0xFFFFFFFFull || max_it == 0 || max_terms == 0)
         return fail(SB200_ERR_INVALID_INPUT, "max_iterations / max_terms must be in [1, 2^32)");
@@ -305,7 +460,13 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
     const int cfg = m->tile_cfg;
     const size_t npart = 2 * (size_t)std::max(std::max(tile_kernel_max_grid(cfg, EPI_PUSH), tile_kernel_max_grid(cfg, EPI_RESID)),
                                               init_state_grid()) + 2;
-    SB_TRY(ws->ensure(p.nloc, p.per * c->world, npart));
+    SB_TRY(ws->ensure(p.nloc, p2p ? 1 : p.per * c->world, npart));
+    if (p2p) {
+        SB_TRY(ensure_arena(c, p.per * c->world));
+        c->epoch_base += 1ull << 24;  // a fresh epoch range per solve
+    }
+    // term ping-pong and the full-length solution mirror: arena vectors (P2P) or workspace buffers (NCCL)
+    double *const T[2] = {p2p ? c->arena.vec(c->rank, 0) : ws->t[0].p, p2p ? c->arena.vec(c->rank, 1) : ws->t[1].p};
 
     // local checks of NeumannState::new, then agree across ranks so that nobody blocks in a collective
     int32_t local_rc = matrix_analyse(mm, opt->mode, false);
@@ -337,25 +498,41 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
     base.ctl = ws->ctl.p;
     base.partials = ws->partials.p;
     base.identity_res = identity;
-    base.defer_tail = multi;
+    base.defer_tail = multi && !p2p;
 
-    // residual over the local rows: allgather x into the term buffer that is dead at this point
-    auto enqueue_resid = [&](uint64_t it, double *scratch_full, int last, int force) -> int32_t {
-        if (multi) {
+    // residual over the local rows. NCCL: allgather x into the term buffer that is dead at this point.
+    // P2P: x was published into every rank's solution mirror by the kernel that produced it (x_published), or is
+    // published here by a copy kernel (after the loop ended / in the spin phase).
+    auto enqueue_resid = [&](uint64_t it, double *scratch_full, int last, int force, bool x_published) -> int32_t {
+        const double *xfull = ws->x.p - p.row0;
+        if (p2p) {
+            if (!x_published) {
+                double *dst[kMaxPeers];
+                for (int q = 0; q < c->world; q++) dst[q] = c->arena.vec(q, 2);
+                SB_TRY(launch_peer_publish(ws->x.p, p.nloc, p.row0, dst, ws->ctl.p, make_px(c, -1, false), force, st));
+                launches++;
+                SB_TRY(peer_wait(c, ws->ctl.p, 0, it, 0, 0, force, nullptr, st));
+            }
+            xfull = c->arena.vec(c->rank, 2);
+        } else if (multi) {
             SB_CUDA(cudaMemcpyAsync(scratch_full + p.row0, ws->x.p, p.nloc * 8, cudaMemcpyDeviceToDevice, st));
             SB_NCCL(g_nccl.AllGather(scratch_full + (uint64_t)c->rank * p.per, scratch_full, p.per, ncclDouble, c->comm, st));
+            xfull = scratch_full;
         }
         TileKernelArgs a = base;
-        a.xin = multi ? scratch_full : ws->x.p - p.row0;
+        a.xin = xfull;
         a.xin_own = ws->x.p;
         a.rhs = resid_rhs;
         a.it = (uint32_t)it;
         a.last_in_iter = last;
         a.force = force;
         a.identity_res = 0;
+        if (p2p) a.px = make_px(c, -1, false);
         launches++;
         SB_TRY(launch_tile_kernel(cfg, EPI_RESID, a, st));
-        if (multi) {
+        if (p2p) {
+            SB_TRY(peer_wait(c, ws->ctl.p, 2, it, last, 0, force, nullptr, st));
+        } else if (multi) {
             SB_NCCL(g_nccl.AllReduce(ws->ctl.p->red, ws->ctl.p->red, 1, ncclDouble, ncclSum, c->comm, st));
             SB_TRY(launch_dist_tail(ws->ctl.p, 2, (uint32_t)it, last, 0, force, nullptr, st));
         }
@@ -373,44 +550,55 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
         ia.b = ws->b.p;
         ia.dinv = dinv;
         ia.c_out = ws->c.p;
-        ia.t_out = ws->t[0].p + p.row0;
+        ia.t_out = T[0] + p.row0;
         ia.x_out = ws->x.p;
         ia.n = (uint32_t)p.nloc;
         ia.compat = compat;
         ia.ctl = ws->ctl.p;
         ia.partials = ws->partials.p;
         ia.identity_res = identity;
-        ia.defer_tail = multi;
+        ia.defer_tail = multi && !p2p;
         const bool resid_due = !identity;
         ia.last_in_iter = !resid_due;
+        ia.row_base = (uint32_t)p.row0;
+        if (p2p) ia.px = make_px(c, 0, resid_due);
         SB_TRY(launch_init_state(ia, st));
         launches++;
-        SB_TRY(exchange_term(c, ws->ctl.p, ws->t[0].p, p.per, st));
-        if (multi) SB_TRY(launch_dist_tail(ws->ctl.p, 1, 0, !resid_due, identity, 0, nullptr, st));
-        if (resid_due) SB_TRY(enqueue_resid(0, ws->t[1].p, 1, 0));
+        if (p2p) {
+            SB_TRY(peer_wait(c, ws->ctl.p, 1, 0, !resid_due, identity, 0, nullptr, st));
+        } else {
+            SB_TRY(exchange_term(c, ws->ctl.p, T[0], p.per, st));
+            if (multi) SB_TRY(launch_dist_tail(ws->ctl.p, 1, 0, !resid_due, identity, 0, nullptr, st));
+        }
+        if (resid_due) SB_TRY(enqueue_resid(0, T[1], 1, 0, true));
     }
     uint64_t it = 1;
     const uint64_t push_end = std::min(max_it, max_terms);
-    const uint64_t kBatch = 4;
+    const uint64_t kBatch = 8;
     bool alive = true;
     while (alive && it < push_end) {
         const uint64_t end = std::min(push_end, it + kBatch);
         for (; it < end; it++) {
             const bool resid_due = !identity && (it % 5 == 0);
             TileKernelArgs a = base;
-            a.xin = ws->t[(it - 1) & 1].p;
+            a.xin = T[(it - 1) & 1];
             a.xin_own = a.xin + p.row0;
-            a.out = ws->t[it & 1].p + p.row0;
+            a.out = T[it & 1] + p.row0;
             a.sol = ws->x.p;
             a.dinv = dinv;
             a.it = (uint32_t)it;
             a.last_in_iter = !resid_due;
+            if (p2p) a.px = make_px(c, (int)(it & 1), resid_due);
             SB_TRY(launch_tile_kernel(cfg, EPI_PUSH, a, st));
             launches++;
-            SB_TRY(exchange_term(c, ws->ctl.p, ws->t[it & 1].p, p.per, st));
-            if (multi) SB_TRY(launch_dist_tail(ws->ctl.p, 1, (uint32_t)it, !resid_due, identity, 0, nullptr, st));
+            if (p2p) {
+                SB_TRY(peer_wait(c, ws->ctl.p, 1, it, !resid_due, identity, 0, nullptr, st));
+            } else {
+                SB_TRY(exchange_term(c, ws->ctl.p, T[it & 1], p.per, st));
+                if (multi) SB_TRY(launch_dist_tail(ws->ctl.p, 1, (uint32_t)it, !resid_due, identity, 0, nullptr, st));
+            }
             // the previous term buffer is dead once this push has run: reuse it as the x allgather target
-            if (resid_due) SB_TRY(enqueue_resid(it, ws->t[(it - 1) & 1].p, 1, 0));
+            if (resid_due) SB_TRY(enqueue_resid(it, T[(it - 1) & 1], 1, 0, true));
         }
         SB_TRY(read_ctl());
         alive = ws->h_ctl->alive != 0;
@@ -422,14 +610,14 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
     uint64_t iterations = ws->h_ctl->iterations;
     const uint64_t terms = ws->h_ctl->terms;
     uint64_t resid_in_loop = 0;
-    double *scratch = ws->t[terms & 1].p;  // current term lives in t[(terms-1)&1]
+    double *scratch = T[terms & 1];  // current term lives in T[(terms-1)&1]
     if (alive && iterations >= max_terms && iterations < max_it) {  // spin phase, see solver.cu
         if (identity) {
             iterations = (ws->h_ctl->res_norm <= opt->tolerance) ? iterations : max_it;
         } else {
             const uint64_t first = (iterations + 4) / 5 * 5;
             if (first < max_it) {
-                SB_TRY(enqueue_resid(first, scratch, 0, 1));
+                SB_TRY(enqueue_resid(first, scratch, 0, 1, false));
                 SB_TRY(read_ctl());
                 resid_in_loop++;
                 const double r = ws->h_ctl->res_norm;
@@ -442,13 +630,15 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
         }
     }
     const bool nonfinite_spin = ws->h_ctl->nonfinite != 0;
-    SB_TRY(enqueue_resid(iterations, scratch, 0, 1));  // final residual (:516)
+    SB_TRY(enqueue_resid(iterations, scratch, 0, 1, false));  // final residual (:516)
     SB_CUDA(cudaEventRecord(ws->ev1, st));
     SB_TRY(read_ctl());
     float dev_ms = 0.f;
     SB_CUDA(cudaEventElapsedTime(&dev_ms, ws->ev0, ws->ev1));
     SB_TRY(copy_d2h(x_local, ws->x.p, p.nloc * 8, st));
     SB_CUDA(cudaStreamSynchronize(st));
+    if (ws->h_ctl->peer_timeout)
+        return fail(SB200_ERR_ALGORITHM, "a peer rank never signalled its exchange (rank died or diverged)");
 
     const LoopCtl &cc = *ws->h_ctl;
     SolveStats stt{};

@@ -176,17 +176,52 @@ __device__ __forceinline__ void tail_logic(LoopCtl *c, int kind, double sum, dou
     if (last_in_iter) end_of_iteration(c, it);
 }
 
+// system-scope flag/slot accessors for the peer exchange
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double *p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// P2P signal: publish this rank's (sum, aux) of the current exchange into every rank's slots, then raise its flag
+// everywhere. Called by one thread after the whole grid's stores are ordered before it (ticket + system fences).
+__device__ __forceinline__ void peer_signal(const LoopCtl *ctl, const PeerExchange &px, double sum, double aux) {
+    const unsigned long long e = px.epoch_base + ctl->xchg + 1ull;
+    const unsigned par = (unsigned)(e & 1ull);
+    for (int p = 0; p < px.world; p++) {
+        double *s = px.slots[p] + ((size_t)par * px.world + px.rank) * 2;
+        st_relaxed_sys_f64(s, sum);
+        st_relaxed_sys_f64(s + 1, aux);
+    }
+    __threadfence_system();
+    for (int p = 0; p < px.world; p++) st_release_sys_u64(px.flags[p] + px.rank, e);
+}
+
 // CTA partial -> global partial array -> the last CTA to arrive sums all partials in index order.
 template <int NT>
 __device__ __forceinline__ void grid_reduce_and_tail(double sq, double aux, LoopCtl *ctl, double *partials, int kind,
                                                      uint32_t it, int last_in_iter, int identity_res, int defer,
-                                                     double *norm_log, double *s_red, int *s_flag) {
+                                                     double *norm_log, double *s_red, int *s_flag,
+                                                     const PeerExchange *px = nullptr) {
+    const bool p2p = px != nullptr && px->world > 1;
+    if (p2p) __threadfence_system();  // this thread's stores into peer memory, before the CTA reports in
     double bs = block_sum<NT>(sq, s_red);
     double ba = identity_res ? block_sum<NT>(aux, s_red) : 0.0;
     if (threadIdx.x == 0) {
         partials[blockIdx.x] = bs;
         if (identity_res) partials[gridDim.x + blockIdx.x] = ba;
-        __threadfence();
+        if (p2p) __threadfence_system(); else __threadfence();
         unsigned t = atomicAdd(&ctl->ticket, 1u);
         *s_flag = (t == gridDim.x - 1);
     }
@@ -201,7 +236,12 @@ __device__ __forceinline__ void grid_reduce_and_tail(double sq, double aux, Loop
         if (identity_res) a = block_sum<NT>(a, s_red);
         if (threadIdx.x == 0) {
             ctl->ticket = 0;
-            tail_logic(ctl, kind, s, a, it, last_in_iter, identity_res, defer, norm_log);
+            if (p2p) {
+                __threadfence_system();
+                peer_signal(ctl, *px, s, a);  // the wait kernel that follows runs tail_logic on the global sums
+            } else {
+                tail_logic(ctl, kind, s, a, it, last_in_iter, identity_res, defer, norm_log);
+            }
         }
     }
 }
@@ -712,6 +752,17 @@ __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
                 const double tn = own - tmp;   // term -= temp         (neumann.rs:294-296)
                 a.out[row] = tn;
                 a.sol[row] = xs + tn;          // solution += term     (neumann.rs:264-266)
+                if (a.px.world > 1) {
+                    // fused exchange: this rank's slice of the new term (and of x when a residual check follows)
+                    // goes straight into every peer's buffers over NVLink, 256 contiguous bytes per warp and peer
+                    const size_t g = (size_t)a.row_base + row;
+                    for (int p = 0; p < a.px.world; p++) {
+                        if (p == a.px.rank || !a.px.t_out[p]) continue;
+                        a.px.t_out[p][g] = tn;
+                        if (a.px.x_out[p]) a.px.x_out[p][g] = xs + tn;
+                    }
+                    if (a.px.x_out[a.px.rank]) a.px.x_out[a.px.rank][g] = xs + tn;
+                }
                 sq += tn * tn;                 // l2_norm accumulation (solver/mod.rs:369-371)
                 if (a.identity_res) {
                     const double r = tn / dv;  // (D o t')_i = (b - A x)_i, SURVEY F12
@@ -725,7 +776,7 @@ __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
     }
     if (EPI != EPI_SPMV) {
         grid_reduce_and_tail<NT>(sq, aux, a.ctl, a.partials, EPI == EPI_PUSH ? TAIL_TERM : TAIL_RESID, a.it,
-                                 a.last_in_iter, a.identity_res, a.defer_tail, a.norm_log, s_red, &s_flag);
+                                 a.last_in_iter, a.identity_res, a.defer_tail, a.norm_log, s_red, &s_flag, &a.px);
     }
 }
 
@@ -874,7 +925,15 @@ __global__ void __launch_bounds__(kInitThreads) init_state_kernel(const InitArgs
             base = a.x0 ? a.x0[i] : 0.0;
         }
         a.t_out[i] = t0;
-        a.x_out[i] = a.skip_term0 ? base : base + t0;  // k = 0: solution += term (neumann.rs:264-266)
+        const double x_new = a.skip_term0 ? base : base + t0;  // k = 0: solution += term (neumann.rs:264-266)
+        a.x_out[i] = x_new;
+        if (a.px.world > 1) {
+            const size_t g = (size_t)a.row_base + i;
+            for (int p = 0; p < a.px.world; p++) {
+                if (p != a.px.rank) a.px.t_out[p][g] = t0;
+                if (a.px.x_out[p]) a.px.x_out[p][g] = x_new;
+            }
+        }
         sq += t0 * t0;
         if (a.identity_res) {
             const double r = t0 / dv;
@@ -882,7 +941,7 @@ __global__ void __launch_bounds__(kInitThreads) init_state_kernel(const InitArgs
         }
     }
     grid_reduce_and_tail<kInitThreads>(sq, aux, a.ctl, a.partials, TAIL_TERM, 0u, a.last_in_iter, a.identity_res,
-                                       a.defer_tail, a.norm_log, s_red, &s_flag);
+                                       a.defer_tail, a.norm_log, s_red, &s_flag, &a.px);
 }
 
 int init_state_grid() { return 148 * 4; }
@@ -912,6 +971,89 @@ __global__ void dist_tail_kernel(LoopCtl *c, int kind, uint32_t it, int last_in_
 int32_t launch_dist_tail(LoopCtl *ctl, int kind, uint32_t it, int last_in_iter, int identity_res, int force,
                          double *norm_log, cudaStream_t stream) {
     dist_tail_kernel<<<1, 1, 0, stream>>>(ctl, kind, it, last_in_iter, identity_res, force, norm_log);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+// P2P exchange, consumer side: one warp. Lane r waits for rank r's flag of the current exchange; lane 0 then adds the
+// ranks' partial sums in rank order (every rank computes the same bits) and runs the loop logic on them.
+__global__ void peer_wait_kernel(LoopCtl *c, const unsigned long long *flags, const double *slots, int world,
+                                 unsigned long long epoch_base, int kind, uint32_t it, int last_in_iter, int identity_res,
+                                 int force, double *norm_log) {
+    if (c->alive == 0 && !force) return;  // dead loop: nobody signalled, nothing to wait for
+    const unsigned long long e = epoch_base + c->xchg + 1ull;
+    const int lane = threadIdx.x;
+    bool ok = true;
+    if (lane < world) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u64(flags + lane) < e) {
+            if (clock64() - t0 > 40000000000ll) {  // ~20 s: a peer died; do not hang the GPU
+                ok = false;
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    if (lane == 0) {
+        if (!ok) {
+            c->peer_timeout = 1;
+            c->alive = 0;
+            return;
+        }
+        const unsigned par = (unsigned)(e & 1ull);
+        double s = 0.0, a = 0.0;
+        for (int r = 0; r < world; r++) {
+            s += ld_relaxed_sys_f64(slots + ((size_t)par * world + r) * 2);
+            a += ld_relaxed_sys_f64(slots + ((size_t)par * world + r) * 2 + 1);
+        }
+        c->xchg += 1;
+        if (kind != TAIL_NONE) tail_logic(c, kind, s, a, it, last_in_iter, identity_res, 0, norm_log);
+    }
+}
+
+int32_t launch_peer_wait(LoopCtl *ctl, const unsigned long long *flags_local, const double *slots_local, int world,
+                         unsigned long long epoch_base, int kind, uint32_t it, int last_in_iter, int identity_res,
+                         int force, double *norm_log, cudaStream_t stream) {
+    peer_wait_kernel<<<1, 32, 0, stream>>>(ctl, flags_local, slots_local, world, epoch_base, kind, it, last_in_iter,
+                                          identity_res, force, norm_log);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+// P2P exchange, plain publish: src[0..n) -> dst_p[offset .. offset+n) on every rank, then signal (no sums).
+struct PublishDst {
+    double *p[kMaxPeers];
+};
+__global__ void __launch_bounds__(256) peer_publish_kernel(const double *__restrict__ src, uint64_t n, uint64_t offset,
+                                                           PublishDst dst, LoopCtl *ctl, PeerExchange px, int force) {
+    __shared__ int s_flag;
+    if (ctl->alive == 0 && !force) return;
+    for (uint64_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (uint64_t)gridDim.x * 256ull) {
+        const double v = src[i];
+        for (int p = 0; p < px.world; p++) dst.p[p][offset + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        unsigned t = atomicAdd(&ctl->ticket, 1u);
+        s_flag = (t == gridDim.x - 1);
+        if (s_flag) {
+            ctl->ticket = 0;
+            __threadfence_system();
+            peer_signal(ctl, px, 0.0, 0.0);
+        }
+    }
+}
+
+int32_t launch_peer_publish(const double *src, uint64_t n, uint64_t offset, double *const *dst, LoopCtl *ctl,
+                            const PeerExchange &px, int force, cudaStream_t stream) {
+    PublishDst d{};
+    for (int p = 0; p < px.world; p++) d.p[p] = dst[p];
+    uint64_t g = (n + 255) / 256;
+    unsigned grid = g > 148ull * 4 ? 148u * 4 : (unsigned)(g ? g : 1);
+    peer_publish_kernel<<<grid, 256, 0, stream>>>(src, n, offset, d, ctl, px, force);
     SB_CUDA(cudaGetLastError());
     return SB200_OK;
 }

@@ -1,0 +1,129 @@
+//! Rust shim over include/sublinear_b200.h — UNBUILT here (no Rust toolchain in the build image); it is the 1:1
+//! mapping a maintainer would add to route `NeumannSolver::solve` / `SparseMatrix` to the B200 library.
+//! Types and traits come from the reference crate (`sublinear`): src/matrix/mod.rs:25-104 (trait Matrix),
+//! src/solver/mod.rs:223-333 (trait SolverAlgorithm), src/solver/mod.rs:22-195, src/error.rs:16-138.
+#![allow(non_camel_case_types)]
+use std::os::raw::c_char;
+
+use sublinear::error::{Result, SolverError};
+use sublinear::solver::{SolverOptions, SolverResult};
+use sublinear::types::{Precision, SolverStats};
+
+#[repr(C)] pub struct sb200_matrix { _p: [u8; 0] }
+#[repr(C)] pub struct sb200_solver { _p: [u8; 0] }
+
+#[repr(C)]
+pub struct sb200_options {
+    pub tolerance: f64, pub max_iterations: u64, pub convergence_mode: i32, pub norm_type: i32,
+    pub collect_stats: i32, pub streaming_interval: u64, pub initial_guess: *const f64, pub initial_guess_len: u64,
+    pub compute_error_bounds: i32, pub error_bounds_tolerance: f64, pub enable_profiling: i32,
+    pub has_random_seed: i32, pub random_seed: u64,
+    pub mode: i32, pub dominance: i32, pub residual_check: i32, pub reserved: i32,
+}
+
+#[repr(C)]
+pub struct sb200_result {
+    pub solution: *mut f64, pub solution_len: u64, pub residual_norm: f64, pub iterations: u64, pub converged: i32,
+    pub has_error_bounds: i32, pub error_upper_bound: f64, pub has_stats: i32, pub total_time_ms: f64,
+    pub matvec_count: u64, pub memory_bytes: u64, pub terms_computed: u64, pub series_converged: i32,
+    pub last_term_norm: f64, pub device_time_ms: f64, pub kernel_launches: u64, pub h2d_bytes: u64, pub d2h_bytes: u64,
+    pub push_kernel_ms: f64, pub push_kernel_count: u64, pub resid_kernel_ms: f64, pub resid_kernel_count: u64,
+}
+
+extern "C" {
+    fn sb200_last_error(buf: *mut c_char, cap: usize) -> usize;
+    fn sb200_matrix_from_triplets(rows: *const u64, cols: *const u64, vals: *const f64, n: u64, nrows: u64, ncols: u64,
+                                  out: *mut *mut sb200_matrix) -> i32;
+    fn sb200_matrix_free(m: *mut sb200_matrix);
+    fn sb200_matrix_multiply_vector(m: *const sb200_matrix, x: *const f64, xlen: u64, y: *mut f64, ylen: u64) -> i32;
+    fn sb200_neumann_new(max_terms: u64, series_tolerance: f64, out: *mut *mut sb200_solver) -> i32;
+    fn sb200_solver_free(s: *mut sb200_solver);
+    fn sb200_options_default(o: *mut sb200_options);
+    fn sb200_solve_into(s: *const sb200_solver, m: *const sb200_matrix, b: *const f64, blen: u64,
+                        opt: *const sb200_options, x_out: *mut f64, out: *mut sb200_result) -> i32;
+}
+
+fn last_error() -> String {
+    let mut buf = vec![0u8; 1024];
+    unsafe { sb200_last_error(buf.as_mut_ptr() as *mut c_char, buf.len()) };
+    String::from_utf8_lossy(&buf).trim_end_matches('\0').to_string()
+}
+
+/// Status code (1-based variant index of `SolverError`, src/error.rs:16-138) -> the Rust error value.
+fn to_error(code: i32, r: &sb200_result, tolerance: f64) -> SolverError {
+    let message = last_error();
+    match code {
+        1 => SolverError::MatrixNotDiagonallyDominant { row: 0, diagonal: 0.0, off_diagonal_sum: 0.0 }, // neumann.rs:164-168
+        2 => SolverError::NumericalInstability { reason: message, iteration: r.iterations as usize, residual_norm: r.residual_norm },
+        3 => SolverError::ConvergenceFailure { iterations: r.iterations as usize, residual_norm: r.residual_norm, tolerance,
+                                               algorithm: "neumann".to_string() },
+        5 => SolverError::DimensionMismatch { expected: 0, actual: 0, operation: message },
+        8 => SolverError::IndexOutOfBounds { index: 0, max_index: 0, context: message },
+        9 => SolverError::InvalidSparseMatrix { reason: message, position: None },
+        4 => SolverError::InvalidInput { message, parameter: None },
+        _ => SolverError::AlgorithmError { algorithm: "neumann".to_string(), message, context: vec![] },
+    }
+}
+
+/// `SparseMatrix` resident on the B200 (same constructor signature as src/matrix/mod.rs:160-164).
+pub struct B200Matrix { h: *mut sb200_matrix, rows: usize, cols: usize }
+unsafe impl Send for B200Matrix {}
+unsafe impl Sync for B200Matrix {}
+
+impl B200Matrix {
+    pub fn from_triplets(triplets: Vec<(usize, usize, Precision)>, rows: usize, cols: usize) -> Result<Self> {
+        let r: Vec<u64> = triplets.iter().map(|t| t.0 as u64).collect();
+        let c: Vec<u64> = triplets.iter().map(|t| t.1 as u64).collect();
+        let v: Vec<f64> = triplets.iter().map(|t| t.2).collect();
+        let mut h = std::ptr::null_mut();
+        let rc = unsafe { sb200_matrix_from_triplets(r.as_ptr(), c.as_ptr(), v.as_ptr(), v.len() as u64, rows as u64, cols as u64, &mut h) };
+        if rc != 0 { return Err(to_error(rc, &unsafe { std::mem::zeroed() }, 0.0)); }
+        Ok(Self { h, rows, cols })
+    }
+    /// `Matrix::multiply_vector` (src/matrix/mod.rs:415-439)
+    pub fn multiply_vector(&self, x: &[Precision], result: &mut [Precision]) -> Result<()> {
+        let rc = unsafe { sb200_matrix_multiply_vector(self.h, x.as_ptr(), x.len() as u64, result.as_mut_ptr(), result.len() as u64) };
+        if rc != 0 { Err(to_error(rc, &unsafe { std::mem::zeroed() }, 0.0)) } else { Ok(()) }
+    }
+    pub fn rows(&self) -> usize { self.rows }
+    pub fn cols(&self) -> usize { self.cols }
+}
+impl Drop for B200Matrix { fn drop(&mut self) { unsafe { sb200_matrix_free(self.h) } } }
+
+/// `NeumannSolver` whose `solve` runs on the B200 (src/solver/neumann.rs:469-555).
+pub struct B200NeumannSolver { h: *mut sb200_solver }
+unsafe impl Send for B200NeumannSolver {}
+unsafe impl Sync for B200NeumannSolver {}
+
+impl B200NeumannSolver {
+    pub fn new(max_terms: usize, series_tolerance: Precision) -> Self {
+        let mut h = std::ptr::null_mut();
+        unsafe { sb200_neumann_new(max_terms as u64, series_tolerance, &mut h) };
+        Self { h }
+    }
+    pub fn default() -> Self { Self::new(50, 1e-8) }
+
+    pub fn solve(&self, matrix: &B200Matrix, b: &[Precision], options: &SolverOptions) -> Result<SolverResult> {
+        let mut o: sb200_options = unsafe { std::mem::zeroed() };
+        unsafe { sb200_options_default(&mut o) };
+        o.tolerance = options.tolerance;
+        o.max_iterations = options.max_iterations as u64;
+        o.collect_stats = options.collect_stats as i32;
+        o.compute_error_bounds = options.compute_error_bounds as i32;
+        if let Some(ref g) = options.initial_guess { o.initial_guess = g.as_ptr(); o.initial_guess_len = g.len() as u64; }
+        let mut x = vec![0.0; b.len()];
+        let mut r: sb200_result = unsafe { std::mem::zeroed() };
+        let rc = unsafe { sb200_solve_into(self.h, matrix.h, b.as_ptr(), b.len() as u64, &o, x.as_mut_ptr(), &mut r) };
+        if rc != 0 { return Err(to_error(rc, &r, options.tolerance)); }
+        let mut res = if r.converged != 0 { SolverResult::success(x, r.residual_norm, r.iterations as usize) }
+                      else { SolverResult::failure(x, r.residual_norm, r.iterations as usize) };
+        if r.has_stats != 0 {
+            let mut s = SolverStats::new();
+            s.total_time_ms = r.total_time_ms;
+            s.matvec_count = r.matvec_count as usize;
+            res.stats = Some(s);
+        }
+        Ok(res)
+    }
+}
+impl Drop for B200NeumannSolver { fn drop(&mut self) { unsafe { sb200_solver_free(self.h) } } }
