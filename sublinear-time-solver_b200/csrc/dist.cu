@@ -544,6 +544,20 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
         return SB200_OK;
     };
 
+    // per-launch events of the push kernels (options.enable_profiling), as in solver.cu
+    struct ProfEv {
+        cudaEvent_t e0, e1;
+        uint64_t it;
+    };
+    std::vector<ProfEv> prof;
+    struct ProfCleanup {
+        std::vector<ProfEv> &v;
+        ~ProfCleanup() {
+            for (auto &q : v) { cudaEventDestroy(q.e0); cudaEventDestroy(q.e1); }
+        }
+    } prof_cleanup{prof};
+    const bool profiling = opt->enable_profiling != 0;
+
     SB_CUDA(cudaEventRecord(ws->ev0, st));
     {
         InitArgs ia{};
@@ -589,7 +603,15 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
             a.it = (uint32_t)it;
             a.last_in_iter = !resid_due;
             if (p2p) a.px = make_px(c, (int)(it & 1), resid_due);
+            if (profiling) {
+                ProfEv q{nullptr, nullptr, it};
+                SB_CUDA(cudaEventCreate(&q.e0));
+                SB_CUDA(cudaEventCreate(&q.e1));
+                SB_CUDA(cudaEventRecord(q.e0, st));
+                prof.push_back(q);
+            }
             SB_TRY(launch_tile_kernel(cfg, EPI_PUSH, a, st));
+            if (profiling) SB_CUDA(cudaEventRecord(prof.back().e1, st));
             launches++;
             if (p2p) {
                 SB_TRY(peer_wait(c, ws->ctl.p, 1, it, !resid_due, identity, 0, nullptr, st));
@@ -672,6 +694,13 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
     out->has_stats = opt->collect_stats != 0;
     out->h2d_bytes = p.nloc * 8;
     out->d2h_bytes = p.nloc * 8;
+    for (auto &q : prof) {
+        if (q.it >= cc.terms) continue;  // launches past the end of the loop were no-ops
+        float ms = 0.f;
+        SB_CUDA(cudaEventElapsedTime(&ms, q.e0, q.e1));
+        out->push_kernel_ms += ms;
+        out->push_kernel_count++;
+    }
     if (stt.nonfinite)
         return fail(SB200_ERR_NUMERICAL_INSTABILITY, "Non-finite residual norm at iteration %llu", (unsigned long long)iterations);
     if (!stt.converged && iterations >= max_it)
