@@ -433,3 +433,43 @@ def test_full_size_properties_c2():
     r3 = s.solve(m, b, sb.SolverOptions(initial_guess=r.solution))
     np.testing.assert_allclose(r3.solution, r.solution, rtol=1e-7)
     assert r3.terms_computed <= 3
+
+
+def test_pagerank_scaled_c3_properties():
+    """Config C3 scaled to n = 1 M / 10 M edges (power-law in-degree, alpha = 0.85, eps = 1e-6): properties only —
+    PageRank fixed point x = rhs + alpha P^T x, mass <= 1 (dangling mass is dropped like the reference does),
+    positivity, and agreement of the solve with a plain power iteration built from the library's own SpMV."""
+    rng = np.random.default_rng(42)
+    n, ne, alpha = 1_000_000, 10_000_000, 0.85
+    src = rng.integers(0, n, ne)
+    dst = np.minimum((rng.pareto(1.1, ne) * 50).astype(np.int64), n - 1)      # heavy hubs: rows with >> 1024 nnz
+    S, rhs = sb.SparseMatrix.pagerank_system(src, dst, n, alpha)
+    assert S.is_diagonally_dominant(sb.DOMINANCE_ROW_OR_COL) and not S.is_diagonally_dominant()
+    opt = sb.SolverOptions(dominance=sb.DOMINANCE_ROW_OR_COL, tolerance=1e-6)
+    r = sb.NeumannSolver.new(200, 1e-9).solve(S, rhs, opt)
+    assert r.converged and (r.solution > 0).all() and r.solution.sum() <= 1.0 + 1e-9
+    res = np.linalg.norm(S.multiply_vector(r.solution) - rhs)
+    assert res <= 1e-6 and abs(res - r.residual_norm) <= 1e-9
+    x = rhs.copy()                                   # power iteration x <- x - (S x - rhs), diagonal of S ~ 1
+    for _ in range(60):
+        x = x - (S.multiply_vector(x) - rhs)
+    np.testing.assert_allclose(r.solution, x, rtol=1e-6, atol=1e-12)
+
+
+def test_solve_entry_batch_scaled_c4():
+    """Config C4 scaled to n = 1 M: 1 024 single-entry queries, eps = 0.01 -> 10 000 walks each (solver.ts:587),
+    checked against the full solve within 5 standard errors; same seed -> same estimates."""
+    n = 1_000_000
+    rp, ci, v, b = sb.gen_bench_csr(n, 1e-5)
+    m = sb.SparseMatrix.from_csr(rp, ci, v, n, n)
+    x = sb.NeumannSolver.default().solve(m, b).solution
+    state, rows = 12345, []
+    for _ in range(1024):                            # rows from the reference's 32-bit LCG (src/core/utils.ts:161-168)
+        state = (state * 1664525 + 1013904223) % 2 ** 32
+        rows.append(state % n)
+    rows = np.asarray(rows)
+    est, var = sb.solve_entry(m, b, rows, eps=0.01, seed=7)
+    se = np.sqrt(var / 10000)
+    assert (np.abs(est - x[rows]) <= 5 * se + 1e-9).all()
+    est2, _ = sb.solve_entry(m, b, rows, eps=0.01, seed=7)
+    assert np.array_equal(est, est2)
