@@ -229,6 +229,55 @@ int32_t sb200_push_iterations_dev(const sb200_matrix *m, const double *b_dev, ui
                                   float *elapsed_ms);
 
 /* ---------------------------------------------------------------------------------------------- */
+/* conjugate gradient on the same SpMV kernel                          */
+/* ---------------------------------------------------------------------------------------------- */
+/* OptimizedSolverConfig (src/optimized_solver.rs:108-127). */
+typedef struct sb200_cg_config {
+    uint64_t max_iterations;   /* 1000 */
+    double tolerance;          /* 1e-6 */
+    int32_t enable_profiling;  /* 0; here: CUDA-event time of every SpMV launch */
+    int32_t reserved;
+} sb200_cg_config;
+
+/* OptimizedSolverResult + OptimizedSolverStats (src/optimized_solver.rs:130-166). */
+typedef struct sb200_cg_result {
+    double *solution;              /* library-owned until sb200_cg_result_free (NULL for *_into / *_dev solves) */
+    uint64_t solution_len;
+    double residual_norm;          /* sqrt(r.r) of the recurrence at exit (:275) */
+    uint64_t iterations;
+    int32_t converged;             /* `rsold <= tolerance^2` seen while iteration < max_iterations (:217-221) */
+    int32_t breakdown;             /* extension: the loop left through |p.Ap| < 1e-16 (:234-236) */
+    double computation_time_ms;
+    uint64_t matvec_count;
+    uint64_t dot_product_count;
+    uint64_t axpy_count;
+    uint64_t total_flops;          /* matvec_count*nnz*2 + iterations*rows*6 (:278-279) */
+    double average_bandwidth_gbs;  /* the reference's own formulas (:281-285) */
+    double average_gflops;
+    /* extensions */
+    double device_time_ms;         /* CUDA-event time of the whole loop */
+    uint64_t kernel_launches;
+    uint64_t h2d_bytes, d2h_bytes;
+    double spmv_kernel_ms;         /* enable_profiling: CUDA-event time of the SpMV launches that did work */
+    uint64_t spmv_kernel_count;
+} sb200_cg_result;
+
+void sb200_cg_config_default(sb200_cg_config *c);
+/* OptimizedConjugateGradientSolver::solve(&matrix, &b) (src/optimized_solver.rs:182-295); the same loop as
+ * FastConjugateGradient::solve (src/fast_solver.rs:126-178) and UltraFastCG::solve (src/ultra_fast.rs:116-158).
+ * x0 = 0; no dominance or symmetry check (the reference has none). "Matrix must be square" ->
+ * SB200_ERR_INVALID_INPUT, length mismatch -> SB200_ERR_DIMENSION_MISMATCH. Not converging is not an error
+ * (converged = 0), as in the reference. */
+int32_t sb200_cg_solve(const sb200_matrix *m, const double *b, uint64_t blen, const sb200_cg_config *cfg,
+                       sb200_cg_result *out);
+int32_t sb200_cg_solve_into(const sb200_matrix *m, const double *b, uint64_t blen, const sb200_cg_config *cfg,
+                            double *x_out, sb200_cg_result *out);
+/* b_dev / x_dev resident in HBM on the matrix's GPU; work is enqueued on `stream`, the call returns after the loop. */
+int32_t sb200_cg_solve_dev(const sb200_matrix *m, const double *b_dev, uint64_t blen, const sb200_cg_config *cfg,
+                           double *x_dev, void *stream, sb200_cg_result *out);
+void sb200_cg_result_free(sb200_cg_result *r);
+
+/* ---------------------------------------------------------------------------------------------- */
 /* single-entry estimation and PageRank (TS-only front doors)               */
 /* ---------------------------------------------------------------------------------------------- */
 /* Batched estimate of x[rows[q]] for A x = b by absorbing random walks (Ulam-von Neumann estimator,

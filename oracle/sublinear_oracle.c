@@ -497,6 +497,71 @@ double orc_push_iterations(const orc_csr *m, const double *b, uint64_t nterms, i
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Conjugate gradient (src/optimized_solver.rs:182-295; fast_solver.rs:126-178; ultra_fast.rs:116-158) */
+/* ------------------------------------------------------------------------------------------ */
+static double cg_dot(const double *x, const double *y, uint64_t n, int variant) {
+    double sum = 0.0;
+    if (variant == ORC_DOT_CHUNK4) { /* fast_solver.rs:180-200 */
+        uint64_t chunks = n / 4;
+        for (uint64_t c = 0; c < chunks; c++) {
+            uint64_t i = c * 4;
+            sum += x[i] * y[i] + x[i + 1] * y[i + 1] + x[i + 2] * y[i + 2] + x[i + 3] * y[i + 3];
+        }
+        for (uint64_t i = chunks * 4; i < n; i++) sum += x[i] * y[i];
+    } else if (variant == ORC_DOT_CHUNK8) { /* ultra_fast.rs:161-185 */
+        uint64_t chunks = n / 8;
+        for (uint64_t c = 0; c < chunks; c++) {
+            uint64_t i = c * 8;
+            sum += x[i] * y[i] + x[i + 1] * y[i + 1] + x[i + 2] * y[i + 2] + x[i + 3] * y[i + 3] +
+                   x[i + 4] * y[i + 4] + x[i + 5] * y[i + 5] + x[i + 6] * y[i + 6] + x[i + 7] * y[i + 7];
+        }
+        for (uint64_t i = chunks * 8; i < n; i++) sum += x[i] * y[i];
+    } else { /* optimized_solver.rs:211-214 */
+        for (uint64_t i = 0; i < n; i++) sum += x[i] * y[i];
+    }
+    return sum;
+}
+
+int orc_cg_solve(const orc_csr *m, const double *b, uint64_t blen, uint64_t max_iterations,
+                 double tolerance, int spmv_variant, int dot_variant, int nthreads, orc_cg_result *res) {
+    if (m->nrows != m->ncols) return ORC_ERR_INVALID_INPUT;      /* :188-190 */
+    if (blen != m->nrows) return ORC_ERR_DIMENSION_MISMATCH;     /* :191-193 */
+    uint64_t n = m->nrows;
+    double *x = res->solution;
+    double *r = (double *)malloc((n ? n : 1) * sizeof(double));
+    double *p = (double *)malloc((n ? n : 1) * sizeof(double));
+    double *ap = (double *)calloc(n ? n : 1, sizeof(double));
+    if (!r || !p || !ap) { free(r); free(p); free(ap); return ORC_ERR_MEMORY_ALLOCATION; }
+    for (uint64_t i = 0; i < n; i++) { x[i] = 0.0; r[i] = b[i]; p[i] = b[i]; } /* :202-208, :215 */
+    uint64_t iteration = 0, matvecs = 0;
+    double tol_sq = tolerance * tolerance;
+    int converged = 0;
+    double rsold = cg_dot(r, r, n, dot_variant);
+    while (iteration < max_iterations) {
+        if (rsold <= tol_sq) { converged = 1; break; }            /* :218-221 */
+        spmv_dispatch(m, p, ap, spmv_variant, nthreads);          /* :224 */
+        matvecs++;
+        double pap = cg_dot(p, ap, n, dot_variant);               /* :228-232 */
+        if (fabs(pap) < 1e-16) break;                             /* :234-236 */
+        double alpha = rsold / pap;
+        for (uint64_t i = 0; i < n; i++) x[i] += alpha * p[i];    /* :241-243 */
+        for (uint64_t i = 0; i < n; i++) r[i] -= alpha * ap[i];   /* :246-248 */
+        double rsnew = cg_dot(r, r, n, dot_variant);
+        double beta = rsnew / rsold;
+        for (uint64_t i = 0; i < n; i++) p[i] = r[i] + beta * p[i]; /* :258-260 */
+        rsold = rsnew;
+        iteration++;
+    }
+    res->residual_norm = sqrt(rsold);
+    res->iterations = iteration;
+    res->converged = converged;
+    res->matvec_count = matvecs;
+    res->total_flops = matvecs * m->nnz * 2 + iteration * n * 6;
+    free(r); free(p); free(ap);
+    return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Generators                                                                                 */
 /* ------------------------------------------------------------------------------------------ */
 

@@ -136,6 +136,27 @@ int orc_neumann_solve(const orc_csr *m, const double *b, uint64_t blen, const or
 double orc_push_iterations(const orc_csr *m, const double *b, uint64_t nterms, int spmv_variant,
                            int nthreads, double *x_out, double *t_out, double *term_norms);
 
+/* ---- conjugate gradient on the same SpMV ----
+ * OptimizedConjugateGradientSolver::solve (src/optimized_solver.rs:182-295); the same loop is
+ * FastConjugateGradient::solve (src/fast_solver.rs:126-178) and UltraFastCG::solve
+ * (src/ultra_fast.rs:116-158), which only differ in the summation order of their dot products. */
+enum {
+    ORC_DOT_SEQUENTIAL = 0, /* `for .. { s += a*b }` (optimized_solver.rs:211-214, 229-232, 248-251) */
+    ORC_DOT_CHUNK4 = 1,     /* sum += (p0+p1+p2+p3) per chunk of 4 (fast_solver.rs:180-200) */
+    ORC_DOT_CHUNK8 = 2      /* sum += (p0+..+p7) per chunk of 8 (ultra_fast.rs:161-185) */
+};
+typedef struct {
+    double *solution;      /* caller-provided buffer of n doubles */
+    double residual_norm;  /* sqrt(rsold) at exit (optimized_solver.rs:275) */
+    uint64_t iterations;
+    int converged;
+    uint64_t matvec_count;
+    uint64_t total_flops;  /* matvec_count*nnz*2 + iterations*rows*6 (optimized_solver.rs:278-279) */
+} orc_cg_result;
+/* Returns ORC_OK, ORC_ERR_INVALID_INPUT ("Matrix must be square") or ORC_ERR_DIMENSION_MISMATCH. */
+int orc_cg_solve(const orc_csr *m, const double *b, uint64_t blen, uint64_t max_iterations,
+                 double tolerance, int spmv_variant, int dot_variant, int nthreads, orc_cg_result *res);
+
 /* ---- synthetic inputs ---- */
 /* create_test_matrix + create_test_rhs (benches/performance_benchmarks.rs:12-43): rows
  * [row0,row1) of the size x size system, emitted as CSR (= from_triplets of the generated triplets). */

@@ -70,6 +70,10 @@ struct DevBuf {
 int32_t copy_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream);
 int32_t copy_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t stream);
 
+// pinned result buffers are recycled (runtime.cu): returns null on allocation failure
+void *pinned_pool_get(size_t bytes);
+void pinned_pool_put(void *p);
+
 // ---- kernel-side contracts -------------------------------------------------------------------------------
 // Tile table entry: tile t covers rows [desc[t].row0, desc[t+1].row0) and nnz [desc[t].nnz0, desc[t+1].nnz0).
 struct TileDesc {
@@ -106,6 +110,13 @@ struct LoopCtl {
     uint32_t ticket;     // last-CTA election
     uint32_t xchg;       // row-partitioned P2P runs: number of exchanges consumed so far (drives epoch + slot parity)
     uint32_t peer_timeout;  // a peer never signalled (the loop is stopped and reported as AlgorithmError)
+    // conjugate gradient on the same kernels (csrc/cg.cu; ref src/optimized_solver.rs:182-295): the scalars of the loop
+    double cg_rsold;     // r^T r of the current residual
+    double cg_pap;       // p^T A p of the latest SpMV
+    double cg_alpha, cg_beta;
+    double cg_tol_sq;    // tolerance^2 (:210)
+    uint32_t cg_converged, cg_breakdown;  // `rsold <= tolerance_sq` seen (:218-221) / |p^T A p| < 1e-16 (:234-236)
+    uint32_t cg_matvecs, cg_pad;
 };
 
 // Row-partitioned runs over peer memory (csrc/dist.cu): every rank maps every other rank's exchange arena (CUDA IPC);
@@ -122,7 +133,7 @@ struct PeerExchange {               // all zero = not used (single GPU, or the N
     unsigned long long *flags[kMaxPeers];  // peer p's flag array [world]
 };
 
-enum Epilogue { EPI_SPMV = 0, EPI_PUSH = 1, EPI_RESID = 2 };
+enum Epilogue { EPI_SPMV = 0, EPI_PUSH = 1, EPI_RESID = 2, EPI_CG = 3 };  // EPI_CG: out = A p and sum p_i (A p)_i (warp-stream kernel only)
 
 struct TileKernelArgs {
     // CSR (device)
@@ -153,6 +164,7 @@ struct TileKernelArgs {
     double *norm_log;     // optional: norm_log[it] = ||t_it||^2 (bare recurrence)
     unsigned long long *phase_log;  // debug ($SUBLINEAR_B200_PHASE_LOG=1): per-phase cycles of thread 0, summed over CTAs
     PeerExchange px;      // row-partitioned P2P exchange (warp-stream kernel only)
+    int probe;            // measurement aid ($SUBLINEAR_B200_WARP_PROBE): 0 = the real kernel
 };
 
 // launchers (kernels.cu). grid = 0 -> persistent grid sized from occupancy.
@@ -199,6 +211,20 @@ int32_t launch_dist_tail(LoopCtl *ctl, int kind, uint32_t it, int last_in_iter, 
 int32_t launch_peer_wait(LoopCtl *ctl, const unsigned long long *flags_local, const double *slots_local, int world,
                          unsigned long long epoch_base, int kind, uint32_t it, int last_in_iter, int identity_res,
                          int force, double *norm_log, cudaStream_t stream);
+// conjugate gradient vector passes (kernels.cu). phase 0: x = 0, r = p = b, rsold = b.b ; phase 1: x += alpha p,
+// r -= alpha ap, rsnew = r.r (then beta, rsold, iteration count and the loop decision in the tail) ; phase 2: p = r + beta p
+struct CgVecArgs {
+    const double *b;   // phase 0
+    double *x, *r, *p;
+    const double *ap;  // phase 1
+    uint64_t n;
+    LoopCtl *ctl;
+    double *partials;
+    int phase;
+};
+int32_t launch_cg_vec(const CgVecArgs &a, cudaStream_t stream);
+int cg_vec_grid();
+
 // P2P exchange: copy this rank's slice src[0..n) to dst[p] + offset on every rank, then signal (kind 0: no sums)
 int32_t launch_peer_publish(const double *src, uint64_t n, uint64_t offset, double *const *dst, LoopCtl *ctl,
                             const PeerExchange &px, int force, cudaStream_t stream);

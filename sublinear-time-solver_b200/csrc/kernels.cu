@@ -149,7 +149,7 @@ __device__ __forceinline__ void end_of_iteration(LoopCtl *c, uint32_t it) {
     if (c->res_norm <= c->tolerance || it + 1 >= c->max_iterations) c->alive = 0;
 }
 
-enum TailKind { TAIL_NONE = 0, TAIL_TERM = 1, TAIL_RESID = 2 };
+enum TailKind { TAIL_NONE = 0, TAIL_TERM = 1, TAIL_RESID = 2, TAIL_CG_INIT = 3, TAIL_CG_PAP = 4, TAIL_CG_RS = 5 };
 
 __device__ __forceinline__ void tail_logic(LoopCtl *c, int kind, double sum, double aux, uint32_t it, int last_in_iter,
                                            int identity_res, int defer, double *norm_log) {
@@ -172,6 +172,23 @@ __device__ __forceinline__ void tail_logic(LoopCtl *c, int kind, double sum, dou
     } else if (kind == TAIL_RESID) {
         c->res_norm2 = sum;
         c->res_norm = sqrt(sum);  // ref :316
+    }
+    else if (kind == TAIL_CG_INIT) {  // rsold = r.r with r = b (optimized_solver.rs:211-215), loop test of iteration 0
+        c->cg_rsold = sum;
+        c->iterations = 0;
+        if (c->max_iterations == 0) c->alive = 0;
+        else if (sum <= c->cg_tol_sq) { c->cg_converged = 1; c->alive = 0; }
+    } else if (kind == TAIL_CG_PAP) {  // :228-238
+        c->cg_pap = sum;
+        c->cg_matvecs += 1;
+        if (fabs(sum) < 1e-16) { c->cg_breakdown = 1; c->alive = 0; }  // `break` before x is touched
+        else c->cg_alpha = c->cg_rsold / sum;
+    } else if (kind == TAIL_CG_RS) {  // :250-264, then the `while` / `if rsold <= tolerance_sq` of the next pass (:217-221)
+        c->cg_beta = sum / c->cg_rsold;
+        c->cg_rsold = sum;
+        c->iterations += 1;
+        if (c->iterations >= c->max_iterations) c->alive = 0;
+        else if (sum <= c->cg_tol_sq) { c->cg_converged = 1; c->alive = 0; }
     }
     if (last_in_iter) end_of_iteration(c, it);
 }
@@ -630,6 +647,7 @@ static int32_t launch_warp_any(Epilogue epi, const TileKernelArgs &a, cudaStream
 
 int32_t launch_tile_kernel(int cfg, Epilogue epi, const TileKernelArgs &a, cudaStream_t stream) {
     if (cfg < 0) return launch_warp_any(epi, a, stream, nullptr);
+    if (epi == EPI_CG) return fail(SB200_ERR_INVALID_INPUT, "the CG epilogue exists in the warp-stream kernel only");
     if (reinterpret_cast<uintptr_t>(a.xin) & 15u)  // 16-byte gathers and the TMA window copy
         return fail(SB200_ERR_INVALID_INPUT, "device vectors must be 16-byte aligned");
     return launch_any(cfg, epi, a, stream, nullptr);
@@ -643,6 +661,61 @@ int tile_kernel_max_grid(int cfg, Epilogue epi) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// per-row epilogue shared by the warp-stream and the SELL kernel: `acc` = (A xin)_row
+// ---------------------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void row_epilogue(const TileKernelArgs &a, uint32_t row, double acc, double own, double dv,
+                                             double xs, double rh, double &sq, double &aux) {
+    if (EPI == EPI_SPMV) {
+        a.out[row] = acc;
+    } else if (EPI == EPI_PUSH) {
+        const double tmp = acc * dv;   // temp *= d_inv        (neumann.rs:289-291)
+        const double tn = own - tmp;   // term -= temp         (neumann.rs:294-296)
+        a.out[row] = tn;
+        a.sol[row] = xs + tn;          // solution += term     (neumann.rs:264-266)
+        if (a.px.world > 1) {
+            // fused exchange: this rank's slice of the new term (and of x when a residual check follows)
+            // goes straight into every peer's buffers over NVLink, 256 contiguous bytes per warp and peer
+            const size_t g = (size_t)a.row_base + row;
+            for (int p = 0; p < a.px.world; p++) {
+                if (p == a.px.rank || !a.px.t_out[p]) continue;
+                a.px.t_out[p][g] = tn;
+                if (a.px.x_out[p]) a.px.x_out[p][g] = xs + tn;
+            }
+            if (a.px.x_out[a.px.rank]) a.px.x_out[a.px.rank][g] = xs + tn;
+        }
+        sq += tn * tn;                 // l2_norm accumulation (solver/mod.rs:369-371)
+        if (a.identity_res) {
+            const double r = tn / dv;  // (D o t')_i = (b - A x)_i, SURVEY F12
+            aux += r * r;
+        }
+    } else if (EPI == EPI_CG) {
+        a.out[row] = acc;              // ap = A p             (optimized_solver.rs:224)
+        sq += own * acc;               // p^T ap               (optimized_solver.rs:228-232)
+    } else {
+        const double r = acc - rh;     // r = A x - rhs        (neumann.rs:308-310)
+        sq += r * r;
+    }
+}
+
+// per-row operands of the epilogue (coalesced: lane r <-> row r)
+template <int EPI>
+__device__ __forceinline__ void row_operands(const TileKernelArgs &a, uint32_t row, double &own, double &dv, double &xs,
+                                             double &rh) {
+    if (EPI == EPI_PUSH) {
+        own = a.xin[a.row_base + row];
+        dv = a.dinv[row];
+        xs = a.sol[row];
+    } else if (EPI == EPI_RESID) {
+        rh = a.rhs[row];
+    } else if (EPI == EPI_CG) {
+        own = a.xin[a.row_base + row];
+    } else if (a.accumulate) {
+        xs = a.out[row];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // the warp-stream kernel (tile configuration -1)
 // ---------------------------------------------------------------------------------------------------------
 // Same three epilogues as the tile kernel, no CTA-level synchronisation at all: every warp owns blocks of 32
@@ -652,10 +725,11 @@ int tile_kernel_max_grid(int cfg, Epilogue epi) {
 // (the reference's order, bit for bit) — 4-5 LSU operations per non-zero instead of the 7 of the staged pipeline,
 // which matters because the load/store pipe, not HBM, is what this access pattern saturates.
 // Lane r <-> row r also makes every epilogue load/store fully coalesced.
-template <int EPI, int NT>
+template <int EPI, int NT, int EPL>
 __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
+    static_assert(EPL == 4 || EPL == 8, "elements per lane and chunk");
     constexpr int WARPS = NT / 32;
-    constexpr uint32_t CH = 128;         // elements per chunk: 4 per lane
+    constexpr uint32_t CH = 32 * EPL;    // elements per chunk: EPL per lane (4: default, 8: twice the gathers in flight)
     constexpr uint32_t kLongRow = 1024;  // a block holding a longer row falls back to warp-per-row sums
     __shared__ __align__(16) double s_prod[WARPS][CH];
     __shared__ double s_red[WARPS];
@@ -683,48 +757,87 @@ __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
         const uint32_t b0 = __shfl_sync(0xffffffffu, rs, 0);
         const uint32_t b1 = __shfl_sync(0xffffffffu, re, (int)(rlast & 31u));
         double own = 0.0, dv = 0.0, xs = 0.0, rh = 0.0;
-        if (active) {
-            if (EPI == EPI_PUSH) {
-                own = a.xin[a.row_base + row];
-                dv = a.dinv[row];
-                xs = a.sol[row];
-            } else if (EPI == EPI_RESID) {
-                rh = a.rhs[row];
-            } else if (a.accumulate) {
-                xs = a.out[row];
-            }
-        }
+        if (active) row_operands<EPI>(a, row, own, dv, xs, rh);
         double acc = (EPI == EPI_SPMV && a.accumulate) ? xs : 0.0;
         const uint32_t max_len = __reduce_max_sync(0xffffffffu, re - rs);
         if (max_len <= kLongRow) {
-            for (uint32_t c0 = b0 & ~3u; c0 < b1; c0 += CH) {
-                const uint32_t e = c0 + 4u * lane;  // this lane's elements e .. e+3 (16-byte aligned slices)
-                double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
-                if (e < b1) {
-                    uint32_t cx, cy, cz, cw;
-                    double v0, v1, v2, v3;
-                    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                                 : "=r"(cx), "=r"(cy), "=r"(cz), "=r"(cw)
-                                 : "l"(a.cols + e), "l"(pol_stream));
-                    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
-                                 : "=d"(v0), "=d"(v1)
-                                 : "l"(a.vals + e), "l"(pol_stream));
-                    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
-                                 : "=d"(v2), "=d"(v3)
-                                 : "l"(a.vals + e + 2), "l"(pol_stream));
+            for (uint32_t c0 = b0 & ~(uint32_t)(EPL - 1); c0 < b1; c0 += CH) {
+                const uint32_t e = c0 + EPL * lane;  // this lane's elements e .. e+EPL-1 (32-byte aligned slices of `values`)
+                double p[EPL];
+#pragma unroll
+                for (int q = 0; q < EPL; q++) p[q] = 0.0;
+                if (e < b1 && (a.probe & 7) != 0) {
+                    // measurement aid ($SUBLINEAR_B200_WARP_PROBE, results are NOT the SpMV): isolates the cost of the
+                    // three phases of a chunk. 1: stream only (no gathers), 2: gathers only (hashed columns, no
+                    // stream), 3: stream + gathers (as 0; the caller also skips the ordered row sums)
+                    uint32_t cx[EPL];
+                    double v[EPL];
+                    if ((a.probe & 7) == 2) {
+#pragma unroll
+                        for (int q = 0; q < EPL; q++) {
+                            uint32_t h = (e + q) * 0x9E3779B9u;
+                            h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
+                            cx[q] = (uint32_t)(h % a.xin_len);
+                            v[q] = 1.0;
+                        }
+                    } else {
+                        if constexpr (EPL == 4) {
+                            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                                         : "=r"(cx[0]), "=r"(cx[1]), "=r"(cx[2]), "=r"(cx[3])
+                                         : "l"(a.cols + e), "l"(pol_stream));
+                        } else {
+                            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                                         : "=r"(cx[0]), "=r"(cx[1]), "=r"(cx[2]), "=r"(cx[3]), "=r"(cx[EPL - 4]), "=r"(cx[EPL - 3]),
+                                           "=r"(cx[EPL - 2]), "=r"(cx[EPL - 1])
+                                         : "l"(a.cols + e), "l"(pol_stream));
+                        }
+#pragma unroll
+                        for (int q = 0; q < EPL; q += 4)
+                            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                                         : "=d"(v[q]), "=d"(v[q + 1]), "=d"(v[q + 2]), "=d"(v[q + 3])
+                                         : "l"(a.vals + e + q), "l"(pol_stream));
+                    }
+#pragma unroll
+                    for (int q = 0; q < EPL; q++)
+                        p[q] = v[q] * ((a.probe & 7) == 1 ? (double)(cx[q] & 1u) : ld_gather(a.xin + cx[q], pol_gather));
+                } else if (e < b1) {
+                    uint32_t cx[EPL];
+                    double v[EPL];
+                    // 256-bit loads (SASS LDG.E.256): the warp reads its slice of `values` contiguously and every
+                    // 32-byte sector is requested from L2 exactly once. (Two 128-bit loads per lane touch each sector
+                    // twice — with L1::no_allocate both requests reach L2, and L2 sector lookups, not DRAM bytes, are
+                    // what bound this kernel on uniform-random columns: DESIGN.md §4.)
+                    if constexpr (EPL == 4) {
+                        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                                     : "=r"(cx[0]), "=r"(cx[1]), "=r"(cx[2]), "=r"(cx[3])
+                                     : "l"(a.cols + e), "l"(pol_stream));
+                    } else {
+                        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                                     : "=r"(cx[0]), "=r"(cx[1]), "=r"(cx[2]), "=r"(cx[3]), "=r"(cx[EPL - 4]), "=r"(cx[EPL - 3]),
+                                       "=r"(cx[EPL - 2]), "=r"(cx[EPL - 1])
+                                     : "l"(a.cols + e), "l"(pol_stream));
+                    }
+#pragma unroll
+                    for (int q = 0; q < EPL; q += 4)
+                        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
+                                     : "=d"(v[q]), "=d"(v[q + 1]), "=d"(v[q + 2]), "=d"(v[q + 3])
+                                     : "l"(a.vals + e + q), "l"(pol_stream));
                     // elements outside [b0,b1) belong to neighbouring rows or to the zero padding: their columns are
                     // valid, their products are never summed
-                    const double x0 = ld_gather(a.xin + cx, pol_gather);
-                    const double x1 = ld_gather(a.xin + cy, pol_gather);
-                    const double x2 = ld_gather(a.xin + cz, pol_gather);
-                    const double x3 = ld_gather(a.xin + cw, pol_gather);
-                    p0 = v0 * x0;
-                    p1 = v1 * x1;
-                    p2 = v2 * x2;
-                    p3 = v3 * x3;
+                    double xg[EPL];
+#pragma unroll
+                    for (int q = 0; q < EPL; q++) xg[q] = ld_gather(a.xin + cx[q], pol_gather);
+#pragma unroll
+                    for (int q = 0; q < EPL; q++) p[q] = v[q] * xg[q];
                 }
-                *reinterpret_cast<double2 *>(sp + 4 * lane) = make_double2(p0, p1);
-                *reinterpret_cast<double2 *>(sp + 4 * lane + 2) = make_double2(p2, p3);
+                if ((a.probe & 7) == 3) {  // measurement aid: no shared-memory pass, no ordered sums
+#pragma unroll
+                    for (int q = 0; q < EPL; q++) acc += p[q];
+                    continue;
+                }
+#pragma unroll
+                for (int q = 0; q < EPL; q += 2)
+                    *reinterpret_cast<double2 *>(sp + EPL * lane + q) = make_double2(p[q], p[q + 1]);
                 __syncwarp();
                 // left-to-right accumulation, the order of CSRStorage::multiply_vector_add (sparse.rs:193-203)
                 const uint32_t lo = max(rs, c0), hi = min(re, c0 + CH);
@@ -744,43 +857,16 @@ __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
                 if ((uint32_t)lane == i) acc += part;
             }
         }
-        if (active) {
-            if (EPI == EPI_SPMV) {
-                a.out[row] = acc;
-            } else if (EPI == EPI_PUSH) {
-                const double tmp = acc * dv;   // temp *= d_inv        (neumann.rs:289-291)
-                const double tn = own - tmp;   // term -= temp         (neumann.rs:294-296)
-                a.out[row] = tn;
-                a.sol[row] = xs + tn;          // solution += term     (neumann.rs:264-266)
-                if (a.px.world > 1) {
-                    // fused exchange: this rank's slice of the new term (and of x when a residual check follows)
-                    // goes straight into every peer's buffers over NVLink, 256 contiguous bytes per warp and peer
-                    const size_t g = (size_t)a.row_base + row;
-                    for (int p = 0; p < a.px.world; p++) {
-                        if (p == a.px.rank || !a.px.t_out[p]) continue;
-                        a.px.t_out[p][g] = tn;
-                        if (a.px.x_out[p]) a.px.x_out[p][g] = xs + tn;
-                    }
-                    if (a.px.x_out[a.px.rank]) a.px.x_out[a.px.rank][g] = xs + tn;
-                }
-                sq += tn * tn;                 // l2_norm accumulation (solver/mod.rs:369-371)
-                if (a.identity_res) {
-                    const double r = tn / dv;  // (D o t')_i = (b - A x)_i, SURVEY F12
-                    aux += r * r;
-                }
-            } else {
-                const double r = acc - rh;     // r = A x - rhs        (neumann.rs:308-310)
-                sq += r * r;
-            }
-        }
+        if (active) row_epilogue<EPI>(a, row, acc, own, dv, xs, rh, sq, aux);
     }
     if (EPI != EPI_SPMV) {
-        grid_reduce_and_tail<NT>(sq, aux, a.ctl, a.partials, EPI == EPI_PUSH ? TAIL_TERM : TAIL_RESID, a.it,
-                                 a.last_in_iter, a.identity_res, a.defer_tail, a.norm_log, s_red, &s_flag, &a.px);
+        const int kind = EPI == EPI_PUSH ? TAIL_TERM : (EPI == EPI_CG ? TAIL_CG_PAP : TAIL_RESID);
+        grid_reduce_and_tail<NT>(sq, aux, a.ctl, a.partials, kind, a.it, a.last_in_iter, a.identity_res, a.defer_tail,
+                                 a.norm_log, s_red, &s_flag, &a.px);
     }
 }
 
-template <int EPI, int NT>
+template <int EPI, int NT, int EPL>
 static int32_t launch_warp_one(const TileKernelArgs &a, cudaStream_t stream, int *max_grid_out) {
     static int max_grid[16] = {0};
     int dev = 0;
@@ -788,7 +874,7 @@ static int32_t launch_warp_one(const TileKernelArgs &a, cudaStream_t stream, int
     if (dev < 0 || dev >= 16) return fail(SB200_ERR_ALGORITHM, "device index %d out of range", dev);
     if (max_grid[dev] == 0) {
         int per_sm = 0, sms = 0;
-        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, warp_kernel<EPI, NT>, NT, 0));
+        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, warp_kernel<EPI, NT, EPL>, NT, 0));
         SB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if (per_sm < 1) return fail(SB200_ERR_ALGORITHM, "warp kernel does not fit on an SM");
         static int cap = [] { const char *e = getenv("SUBLINEAR_B200_WARP_CTAS"); return e ? atoi(e) : 0; }();
@@ -804,16 +890,30 @@ static int32_t launch_warp_one(const TileKernelArgs &a, cudaStream_t stream, int
     unsigned need = (nblocks + NT / 32 - 1) / (NT / 32);
     unsigned grid = need < (unsigned)max_grid[dev] ? need : (unsigned)max_grid[dev];
     if (grid == 0) grid = 1;
-    warp_kernel<EPI, NT><<<grid, NT, 0, stream>>>(a);
+    static int probe = [] { const char *e = getenv("SUBLINEAR_B200_WARP_PROBE"); return e ? atoi(e) : 0; }();
+    TileKernelArgs ap = a;
+    ap.probe = probe;
+    warp_kernel<EPI, NT, EPL><<<grid, NT, 0, stream>>>(ap);
     SB_CUDA(cudaGetLastError());
     return SB200_OK;
 }
 
 static int32_t launch_warp_any(Epilogue epi, const TileKernelArgs &a, cudaStream_t stream, int *mg) {
+    // elements per lane and chunk: 4 (default) or 8 ($SUBLINEAR_B200_WARP_EPL; measurement aid, same results bit for bit)
+    static int epl = [] { const char *e = getenv("SUBLINEAR_B200_WARP_EPL"); return (e && atoi(e) == 8) ? 8 : 4; }();
+    if (epl == 8) {
+        switch (epi) {
+            case EPI_SPMV: return launch_warp_one<EPI_SPMV, 256, 8>(a, stream, mg);
+            case EPI_PUSH: return launch_warp_one<EPI_PUSH, 256, 8>(a, stream, mg);
+            case EPI_CG: return launch_warp_one<EPI_CG, 256, 8>(a, stream, mg);
+            default: return launch_warp_one<EPI_RESID, 256, 8>(a, stream, mg);
+        }
+    }
     switch (epi) {
-        case EPI_SPMV: return launch_warp_one<EPI_SPMV, 256>(a, stream, mg);
-        case EPI_PUSH: return launch_warp_one<EPI_PUSH, 256>(a, stream, mg);
-        default: return launch_warp_one<EPI_RESID, 256>(a, stream, mg);
+        case EPI_SPMV: return launch_warp_one<EPI_SPMV, 256, 4>(a, stream, mg);
+        case EPI_PUSH: return launch_warp_one<EPI_PUSH, 256, 4>(a, stream, mg);
+        case EPI_CG: return launch_warp_one<EPI_CG, 256, 4>(a, stream, mg);
+        default: return launch_warp_one<EPI_RESID, 256, 4>(a, stream, mg);
     }
 }
 
@@ -1054,6 +1154,53 @@ int32_t launch_peer_publish(const double *src, uint64_t n, uint64_t offset, doub
     uint64_t g = (n + 255) / 256;
     unsigned grid = g > 148ull * 4 ? 148u * 4 : (unsigned)(g ? g : 1);
     peer_publish_kernel<<<grid, 256, 0, stream>>>(src, n, offset, d, ctl, px, force);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// conjugate gradient vector passes (ref src/optimized_solver.rs:202-215, 240-260). HBM-bound streaming kernels:
+// phase 1 moves 48 B/row, phase 2 24 B/row; products and sums stay separate IEEE operations (-fmad=false).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kCgThreads = 256;
+
+__global__ void __launch_bounds__(kCgThreads) cg_vec_kernel(const CgVecArgs a) {
+    __shared__ double s_red[kCgThreads / 32];
+    __shared__ int s_flag;
+    if (a.phase != 0 && a.ctl->alive == 0) return;  // loop already finished: no-op launch
+    const uint64_t stride = (uint64_t)gridDim.x * kCgThreads;
+    double sq = 0.0;
+    if (a.phase == 0) {
+        for (uint64_t i = blockIdx.x * (uint64_t)kCgThreads + threadIdx.x; i < a.n; i += stride) {
+            const double bi = a.b[i];
+            a.x[i] = 0.0;
+            a.r[i] = bi;
+            a.p[i] = bi;
+            sq += bi * bi;
+        }
+        grid_reduce_and_tail<kCgThreads>(sq, 0.0, a.ctl, a.partials, TAIL_CG_INIT, 0u, 0, 0, 0, nullptr, s_red, &s_flag);
+    } else if (a.phase == 1) {
+        const double alpha = a.ctl->cg_alpha;
+        for (uint64_t i = blockIdx.x * (uint64_t)kCgThreads + threadIdx.x; i < a.n; i += stride) {
+            a.x[i] = a.x[i] + alpha * a.p[i];        // x += alpha p   (:241-243)
+            const double ri = a.r[i] - alpha * a.ap[i];  // r -= alpha ap  (:246-248)
+            a.r[i] = ri;
+            sq += ri * ri;                           // rsnew          (:250-253)
+        }
+        grid_reduce_and_tail<kCgThreads>(sq, 0.0, a.ctl, a.partials, TAIL_CG_RS, 0u, 0, 0, 0, nullptr, s_red, &s_flag);
+    } else {
+        const double beta = a.ctl->cg_beta;
+        for (uint64_t i = blockIdx.x * (uint64_t)kCgThreads + threadIdx.x; i < a.n; i += stride)
+            a.p[i] = a.r[i] + beta * a.p[i];         // p = r + beta p (:258-260)
+    }
+}
+
+int cg_vec_grid() { return 148 * 8; }
+
+int32_t launch_cg_vec(const CgVecArgs &a, cudaStream_t stream) {
+    uint64_t g = (a.n + kCgThreads - 1) / kCgThreads;
+    unsigned grid = g > (uint64_t)cg_vec_grid() ? (unsigned)cg_vec_grid() : (unsigned)(g ? g : 1);
+    cg_vec_kernel<<<grid, kCgThreads, 0, stream>>>(a);
     SB_CUDA(cudaGetLastError());
     return SB200_OK;
 }

@@ -143,6 +143,46 @@ int32_t copy_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t
     return SB200_OK;
 }
 
+// pinned result buffers are recycled: cudaHostAlloc of 80 MB costs more than a whole solve
+namespace {
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<std::pair<void *, size_t>> free_list;
+    void *get(size_t bytes) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (size_t i = 0; i < free_list.size(); i++)
+            if (free_list[i].second >= bytes && free_list[i].second <= 2 * bytes + 4096) {
+                void *p = free_list[i].first;
+                sizes_.push_back({p, free_list[i].second});
+                free_list.erase(free_list.begin() + i);
+                return p;
+            }
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        sizes_.push_back({p, bytes});
+        return p;
+    }
+    void put(void *p) {
+        std::lock_guard<std::mutex> lk(mu);
+        for (size_t i = 0; i < sizes_.size(); i++)
+            if (sizes_[i].first == p) {
+                if (free_list.size() < 4) free_list.push_back(sizes_[i]);
+                else cudaFreeHost(p);
+                sizes_.erase(sizes_.begin() + i);
+                return;
+            }
+    }
+    std::vector<std::pair<void *, size_t>> sizes_;
+};
+PinnedPool g_pinned;
+}  // namespace
+
+void *pinned_pool_get(size_t bytes) { return g_pinned.get(bytes); }
+void pinned_pool_put(void *p) { g_pinned.put(p); }
+
 }  // namespace sb200
 
 using namespace sb200;

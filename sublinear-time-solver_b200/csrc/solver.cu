@@ -20,42 +20,6 @@ static double wall_ms() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-// pinned result buffers are recycled: cudaHostAlloc of 80 MB costs more than a whole solve
-namespace {
-struct PinnedPool {
-    std::mutex mu;
-    std::vector<std::pair<void *, size_t>> free_list;
-    void *get(size_t bytes) {
-        std::lock_guard<std::mutex> lk(mu);
-        for (size_t i = 0; i < free_list.size(); i++)
-            if (free_list[i].second >= bytes && free_list[i].second <= 2 * bytes + 4096) {
-                void *p = free_list[i].first;
-                sizes_.push_back({p, free_list[i].second});
-                free_list.erase(free_list.begin() + i);
-                return p;
-            }
-        void *p = nullptr;
-        if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        sizes_.push_back({p, bytes});
-        return p;
-    }
-    void put(void *p) {
-        std::lock_guard<std::mutex> lk(mu);
-        for (size_t i = 0; i < sizes_.size(); i++)
-            if (sizes_[i].first == p) {
-                if (free_list.size() < 4) free_list.push_back(sizes_[i]);
-                else cudaFreeHost(p);
-                sizes_.erase(sizes_.begin() + i);
-                return;
-            }
-    }
-    std::vector<std::pair<void *, size_t>> sizes_;
-};
-PinnedPool g_pinned;
-}  // namespace
 
 int32_t validate_options(const sb200_options *opt) {
     if (!opt) return fail(SB200_ERR_INVALID_INPUT, "options is null");
@@ -418,7 +382,7 @@ static int32_t solve_host(const sb200_solver *s, const sb200_matrix *m, const do
     SB_TRY(solve_device(s, mm, ws->b.p, x0.p, opt, ws->x.p, st, *ws, stats));
     double *dst = x_out;
     if (own_solution) {
-        dst = (double *)g_pinned.get(n * 8);
+        dst = (double *)pinned_pool_get(n * 8);
         if (!dst) return fail(SB200_ERR_MEMORY_ALLOCATION, "pinned allocation of %llu bytes failed", (unsigned long long)(n * 8));
         out->solution = dst;
         out->solution_len = n;
@@ -534,7 +498,7 @@ int32_t sb200_solve_dev(const sb200_solver *s, const sb200_matrix *m, const doub
 
 void sb200_result_free(sb200_result *r) {
     if (!r) return;
-    if (r->solution) g_pinned.put(r->solution);
+    if (r->solution) pinned_pool_put(r->solution);
     r->solution = nullptr;
     r->solution_len = 0;
 }
