@@ -326,6 +326,9 @@ def main():
     nnz_local = m.nnz()
     peak, peak_src = measured_peak()
     roofline = None
+    layout = m.storage_info()
+    kernel_name = ("sell_kernel<EPI_PUSH,256,8> (SELL-32 layout, no shared memory)" if layout["layout"] == sb.LAYOUT_SELL32
+                   else "warp_kernel<EPI_PUSH,256,4> (CSR slices)")
     if push_cnt:
         t_push = push_ms / push_cnt * 1e-3
         alg = algorithmic_bytes_push(n_local, nnz_local) + (8 * (size - n_local) if dist else 0)
@@ -338,7 +341,7 @@ def main():
         except Exception:
             pass
         roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "kernel": "warp_kernel<EPI_PUSH,256>", "avg_launch_us": t_push * 1e6,
+                    "traffic": traffic, "kernel": kernel_name, "avg_launch_us": t_push * 1e6,
                     "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                     "frac_of_nominal_8TBs": ach / 8000.0, "push_share_of_step": push_ms / (ms_total if not dist else wall),
                     "resid_kernel_avg_us": (res_ms / res_cnt * 1e3) if res_cnt else None,
@@ -392,7 +395,9 @@ def main():
                        "iterations_per_step": r_last.iterations, "converged": r_last.converged,
                        "l2_policy": "inputs larger than L2 (1.2 GB CSR stream per SpMV vs 126 MB L2), no flush",
                        "parallelism": "single GPU" if not dist else f"row blocks x{world}, NCCL allgather of the term slice per term",
-                       "rel_residual": rel_res, "setup_s": t_gen},
+                       "rel_residual": rel_res, "setup_s": t_gen,
+                       "device_layout": "SELL-32" if layout["layout"] == sb.LAYOUT_SELL32 else "CSR",
+                       "value_slots_streamed_per_spmv": layout["slots"], "matrix_device_bytes": layout["device_bytes"]},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_local * world if dist else 8 * n_local,
                     "d2h_bytes_per_step": 8 * n_local * world if dist else 8 * n_local, "ms_per_step": e2e_s / args.steps * 1e3,

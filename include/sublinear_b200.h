@@ -171,6 +171,12 @@ int32_t sb200_matrix_nnz(const sb200_matrix *m, uint64_t *out);
 int32_t sb200_matrix_get(const sb200_matrix *m, uint64_t row, uint64_t col, double *value, int32_t *present);
 int32_t sb200_matrix_is_diagonally_dominant(const sb200_matrix *m, int32_t dominance, int32_t *out);
 int32_t sb200_matrix_diagonal_dominance_factor(const sb200_matrix *m, double *factor, int32_t *present);
+/* Device layout the hot kernels read (extension; the CSRStorage slices stay the ingest / export format):
+ * layout 0 = the CSR slices as uploaded, 1 = an additional SELL-32 copy (blocks of 32 rows, element k of row r at
+ * slab*32 + k*32 + r, zero-padded to the longest row of the block) chosen when it costs <= 25 % extra slots.
+ * slots = value slots the kernels stream per SpMV (= nnz for layout 0); device_bytes = all matrix arrays. */
+enum { SB200_LAYOUT_CSR = 0, SB200_LAYOUT_SELL32 = 1 };
+int32_t sb200_matrix_storage_info(const sb200_matrix *m, int32_t *layout, uint64_t *slots, uint64_t *device_bytes);
 /* CSRStorage::to_triplets / SparseMatrix::as_csr (src/matrix/sparse.rs:210-227, mod.rs:313-319): copy out.
  * Any output pointer may be NULL. row_ptr has nrows+1 entries. */
 int32_t sb200_matrix_export_csr(const sb200_matrix *m, uint64_t *row_ptr, uint32_t *col_indices, double *values);
@@ -227,6 +233,64 @@ void sb200_result_free(sb200_result *r);
 int32_t sb200_push_iterations_dev(const sb200_matrix *m, const double *b_dev, uint64_t blen, uint64_t nterms,
                                   double *x_dev, double *t_dev, double *term_norms, void *stream,
                                   float *elapsed_ms);
+
+/* ---------------------------------------------------------------------------------------------- */
+/* SolverAlgorithm state interface and streaming                                */
+/* ---------------------------------------------------------------------------------------------- */
+/* trait SolverAlgorithm { initialize, step, is_converged, extract_solution, update_rhs } (src/solver/mod.rs:223-252)
+ * and trait SolverState { residual_norm, matvec_count, error_bounds, memory_usage, reset } (:336-352) for
+ * NeumannSolver / NeumannState (src/solver/neumann.rs:97-135, 350-462). The state shares ownership of its matrix
+ * handle: sb200_matrix_free and sb200_state_free may be called in either order. */
+typedef struct sb200_state sb200_state;
+enum { SB200_STEP_CONTINUE = 0, SB200_STEP_CONVERGED = 1 }; /* StepResult (src/solver/mod.rs:355-363) */
+typedef struct sb200_state_info_t {
+    uint64_t dimension;
+    double residual_norm;      /* +inf until the first step */
+    uint64_t matvec_count;
+    uint64_t terms_computed;
+    int32_t series_converged;
+    double last_term_norm;
+    int32_t has_error_bounds;  /* estimate_error_bounds (neumann.rs:321-347), when adaptive_truncation */
+    double error_upper_bound;
+    uint64_t memory_bytes;
+} sb200_state_info_t;
+/* initialize = NeumannState::new (neumann.rs:139-249): same checks and errors as sb200_solve; no term is added. */
+int32_t sb200_neumann_initialize(const sb200_solver *s, const sb200_matrix *m, const double *b, uint64_t blen,
+                                 const sb200_options *opt, sb200_state **out);
+/* step: the reference's own step() fails for lack of a matrix reference (neumann.rs:390-403); this runs the body it
+ * left commented out (:404-418): compute_next_term, update_residual, estimate_error_bounds;
+ * *step_result = CONVERGED once series_converged or terms_computed >= max_terms.
+ * SB200_ERR_NUMERICAL_INSTABILITY on a non-finite residual (solver/mod.rs:271-279). */
+int32_t sb200_state_step(sb200_state *st, int32_t *step_result);
+int32_t sb200_state_is_converged(const sb200_state *st, int32_t *out);             /* neumann.rs:422-430 */
+int32_t sb200_state_extract_solution(const sb200_state *st, double *x, uint64_t xlen); /* :432-434 */
+/* update_rhs(&mut state, &[(index, delta)]) (neumann.rs:436-462). SB200_MODE_REF_COMPAT: the literal code (the scaled
+ * delta goes into rhs AND the solution, the series restarts from the whole new rhs). SB200_MODE_CORRECT: the
+ * incremental solve its comment asks for — the series restarts from D^-1 delta_b, so further steps add
+ * A^-1 delta_b to the solution already held. SB200_ERR_INDEX_OUT_OF_BOUNDS leaves the state untouched. */
+int32_t sb200_state_update_rhs(sb200_state *st, const uint64_t *indices, const double *deltas, uint64_t count);
+int32_t sb200_state_reset(sb200_state *st);                                         /* neumann.rs:367-378 */
+int32_t sb200_state_info(const sb200_state *st, sb200_state_info_t *info);
+void sb200_state_free(sb200_state *st);
+
+/* PartialSolution (src/solver/mod.rs:198-217), handed to the callback every options.streaming_interval iterations of
+ * sb200_solve_streaming; `solution` points to library-owned pinned host memory valid during the call only. */
+typedef struct sb200_partial_solution {
+    uint64_t iteration;
+    const double *solution;
+    uint64_t solution_len;
+    double residual_norm;          /* latest evaluated residual (+inf before the first evaluation) */
+    int32_t converged;
+    int32_t has_estimated_remaining;
+    uint64_t estimated_remaining;  /* terms until ||t|| < series_tolerance at the observed contraction rate */
+    double timestamp_ms;           /* since the call started */
+} sb200_partial_solution;
+/* return non-zero to stop the solve after this partial solution */
+typedef int32_t (*sb200_stream_callback)(const sb200_partial_solution *partial, void *user);
+/* NeumannSolver::solve with SolverOptions::streaming(interval) (src/solver/mod.rs:100-116); the callback shape follows
+ * WasmSublinearSolver::solve_stream (src/wasm_iface.rs:119-166). streaming_interval = 0 -> plain sb200_solve. */
+int32_t sb200_solve_streaming(const sb200_solver *s, const sb200_matrix *m, const double *b, uint64_t blen,
+                              const sb200_options *opt, sb200_stream_callback callback, void *user, sb200_result *out);
 
 /* ---------------------------------------------------------------------------------------------- */
 /* conjugate gradient on the same SpMV kernel                          */

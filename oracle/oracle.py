@@ -27,6 +27,7 @@ ERR_INVALID_SPARSE_MATRIX = 9
 MODE_CORRECT, MODE_REF_COMPAT = 0, 1
 DOM_ROW, DOM_ROW_OR_COL = 0, 1
 SPMV_SCALAR, SPMV_SIMD4, SPMV_PARALLEL = 0, 1, 2
+DOT_SEQUENTIAL, DOT_CHUNK4, DOT_CHUNK8 = 0, 1, 2
 
 
 class _Csr(C.Structure):
@@ -50,6 +51,11 @@ class _Result(C.Structure):
                 ("matvec_count", C.c_uint64), ("converged", C.c_int), ("series_converged", C.c_int),
                 ("has_error_bound", C.c_int), ("error_bound", C.c_double),
                 ("last_term_norm", C.c_double), ("total_time_ms", C.c_double)]
+
+
+class _CgResult(C.Structure):
+    _fields_ = [("solution", C.POINTER(C.c_double)), ("residual_norm", C.c_double), ("iterations", C.c_uint64),
+                ("converged", C.c_int), ("matvec_count", C.c_uint64), ("total_flops", C.c_uint64)]
 
 
 def build(fast: bool = False, out_dir: str | None = None) -> str:
@@ -101,6 +107,20 @@ def lib(fast: bool = False, out_dir: str | None = None):
     L.orc_neumann_solve.argtypes = [C.POINTER(_Csr), f64p, C.c_uint64, C.POINTER(_Options), C.POINTER(_Result)]
     L.orc_push_iterations.argtypes = [C.POINTER(_Csr), f64p, C.c_uint64, C.c_int, C.c_int, f64p, f64p, f64p]
     L.orc_push_iterations.restype = C.c_double
+    L.orc_state_new.argtypes = [C.POINTER(_Csr), f64p, C.c_uint64, C.POINTER(_Options), C.POINTER(C.c_void_p)]
+    L.orc_state_step.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    L.orc_state_is_converged.argtypes = [C.c_void_p]
+    L.orc_state_solution.argtypes = [C.c_void_p, f64p]
+    L.orc_state_solution.restype = None
+    L.orc_state_update_rhs.argtypes = [C.c_void_p, u64p, f64p, C.c_uint64]
+    L.orc_state_reset.argtypes = [C.c_void_p]
+    L.orc_state_reset.restype = None
+    L.orc_state_info.argtypes = [C.c_void_p, f64p, u64p, u64p, C.POINTER(C.c_int), f64p, C.POINTER(C.c_int), f64p]
+    L.orc_state_info.restype = None
+    L.orc_state_free.argtypes = [C.c_void_p]
+    L.orc_state_free.restype = None
+    L.orc_cg_solve.argtypes = [C.POINTER(_Csr), f64p, C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_int,
+                               C.POINTER(_CgResult)]
     L.orc_gen_bench_k.argtypes = [C.c_uint64, C.c_double]
     L.orc_gen_bench_k.restype = C.c_uint64
     L.orc_gen_bench_csr.argtypes = [C.c_uint64, C.c_double, C.c_uint64, C.c_uint64, C.POINTER(_Csr), f64p]
@@ -254,6 +274,95 @@ def neumann_solve(m: Csr, b, *, tolerance=1e-6, max_iterations=1000, initial_gue
     return Result(x, r.residual_norm, int(r.iterations), int(r.terms_computed), int(r.matvec_count),
                   bool(r.converged), bool(r.series_converged),
                   r.error_bound if r.has_error_bound else None, r.last_term_norm, r.total_time_ms, rc)
+
+
+class NeumannState:
+    """SolverAlgorithm::{initialize, step, is_converged, extract_solution, update_rhs} + SolverState::reset restated
+    (src/solver/mod.rs:223-252, src/solver/neumann.rs:350-462); step() is the body the reference left commented out."""
+
+    def __init__(self, m: Csr, b, *, tolerance=1e-6, initial_guess=None, max_terms=50, series_tolerance=1e-8,
+                 adaptive_truncation=True, mode=MODE_CORRECT, dominance=DOM_ROW, spmv_variant=SPMV_SCALAR):
+        L = lib()
+        self._L, self._m, self._mc = L, m, m.c()     # keep the arrays the C state points into alive
+        b = _f64(b)
+        o = _Options()
+        L.orc_options_default(C.byref(o))
+        o.tolerance, o.max_terms, o.series_tolerance = tolerance, max_terms, series_tolerance
+        o.adaptive_truncation, o.mode, o.dominance, o.spmv_variant = int(adaptive_truncation), mode, dominance, spmv_variant
+        if initial_guess is not None:
+            ig = _f64(initial_guess)
+            o.initial_guess, o.initial_guess_len = _p(ig, C.c_double), len(ig)
+        self._h = C.c_void_p()
+        rc = L.orc_state_new(C.byref(self._mc), _p(b, C.c_double), len(b), C.byref(o), C.byref(self._h))
+        if rc != OK:
+            self._h = None
+            raise OracleError(rc, "state_new")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orc_state_free(self._h)
+            self._h = None
+
+    def step(self):
+        out = C.c_int()
+        rc = self._L.orc_state_step(self._h, C.byref(out))
+        if rc != OK:
+            raise OracleError(rc, "state_step")
+        return out.value
+
+    def is_converged(self):
+        return bool(self._L.orc_state_is_converged(self._h))
+
+    def extract_solution(self):
+        x = np.zeros(self._m.nrows)
+        self._L.orc_state_solution(self._h, _p(x, C.c_double))
+        return x
+
+    def update_rhs(self, delta_b):
+        idx = _u64([i for i, _ in delta_b])
+        dl = _f64([d for _, d in delta_b])
+        rc = self._L.orc_state_update_rhs(self._h, _p(idx, C.c_uint64), _p(dl, C.c_double), len(dl))
+        if rc != OK:
+            raise OracleError(rc, "update_rhs")
+
+    def reset(self):
+        self._L.orc_state_reset(self._h)
+
+    def info(self):
+        rn, tn, bd = C.c_double(), C.c_double(), C.c_double()
+        mv, tc = C.c_uint64(), C.c_uint64()
+        sc, hb = C.c_int(), C.c_int()
+        self._L.orc_state_info(self._h, C.byref(rn), C.byref(mv), C.byref(tc), C.byref(sc), C.byref(tn), C.byref(hb), C.byref(bd))
+        return {"residual_norm": rn.value, "matvec_count": mv.value, "terms_computed": tc.value,
+                "series_converged": bool(sc.value), "last_term_norm": tn.value,
+                "error_upper_bound": bd.value if hb.value else None}
+
+
+@dataclass
+class CgResult:
+    solution: np.ndarray
+    residual_norm: float
+    iterations: int
+    converged: bool
+    matvec_count: int
+    total_flops: int
+
+
+def cg_solve(m: Csr, b, *, max_iterations=1000, tolerance=1e-6, spmv_variant=SPMV_SCALAR,
+             dot_variant=DOT_SEQUENTIAL, nthreads=0, fast=False) -> CgResult:
+    """OptimizedConjugateGradientSolver::solve (src/optimized_solver.rs:182-295) / FastConjugateGradient /
+    UltraFastCG restated; dot_variant selects the summation order of the three reference variants."""
+    L = lib(fast)
+    b = _f64(b)
+    x = np.zeros(m.nrows)
+    r = _CgResult()
+    r.solution = _p(x, C.c_double)
+    mc = m.c()
+    rc = L.orc_cg_solve(C.byref(mc), _p(b, C.c_double), len(b), max_iterations, tolerance, spmv_variant, dot_variant,
+                        nthreads, C.byref(r))
+    if rc != OK:
+        raise OracleError(rc, "cg_solve")
+    return CgResult(x, r.residual_norm, int(r.iterations), bool(r.converged), int(r.matvec_count), int(r.total_flops))
 
 
 def push_iterations(m: Csr, b, nterms, spmv_variant=SPMV_SCALAR, nthreads=0, fast=False):

@@ -304,6 +304,8 @@ typedef struct {
     const orc_csr *m;
     uint64_t n;
     double *solution, *rhs, *residual, *dinv, *term, *temp;
+    double *b;               /* own copy of the right-hand side (update_rhs changes it) */
+    int mode;
     const double *resid_rhs; /* c in ref_compat, b in correct mode */
     double residual_norm, term_norm, rhs_norm;
     uint64_t terms, matvec, max_terms;
@@ -360,11 +362,10 @@ static int is_converged(const nstate *s) {
     return residual_converged || (s->series_converged && !max_terms_reached);
 }
 
-int orc_neumann_solve(const orc_csr *m, const double *b, uint64_t blen, const orc_options *opt,
-                      orc_result *res) {
-    double t_start = now_s();
+/* NeumannState::new (src/solver/neumann.rs:139-249). Allocates; the caller releases with state_release. */
+static int state_init(nstate *sp, const orc_csr *m, const double *b, uint64_t blen, const orc_options *opt) {
     uint64_t n = m->nrows;
-    /* NeumannState::new (src/solver/neumann.rs:139-249) */
+    memset(sp, 0, sizeof(*sp));
     if (m->nrows != m->ncols) return ORC_ERR_INVALID_INPUT;          /* :147-152 */
     if (blen != n) return ORC_ERR_DIMENSION_MISMATCH;                /* :154-160 */
     int dd = orc_is_diagonally_dominant(m, NULL);                    /* :163-169 */
@@ -375,6 +376,7 @@ int orc_neumann_solve(const orc_csr *m, const double *b, uint64_t blen, const or
     memset(&s, 0, sizeof(s));
     s.m = m;
     s.n = n;
+    s.mode = opt->mode;
     size_t bytes = (n ? n : 1) * sizeof(double);
     s.solution = (double *)malloc(bytes);
     s.rhs = (double *)malloc(bytes);
@@ -382,11 +384,13 @@ int orc_neumann_solve(const orc_csr *m, const double *b, uint64_t blen, const or
     s.dinv = (double *)calloc(n ? n : 1, sizeof(double));
     s.term = (double *)malloc(bytes);
     s.temp = (double *)malloc(bytes);
+    s.b = (double *)malloc(bytes);
     int rc = ORC_OK;
-    if (!s.solution || !s.rhs || !s.residual || !s.dinv || !s.term || !s.temp) {
+    if (!s.solution || !s.rhs || !s.residual || !s.dinv || !s.term || !s.temp || !s.b) {
         rc = ORC_ERR_MEMORY_ALLOCATION;
-        goto done;
+        goto fail;
     }
+    memcpy(s.b, b, n * sizeof(double));
     for (uint64_t i = 0; i < n; i++) { /* :172-188 */
         double d;
         if (orc_csr_get(m, i, i, &d)) {
@@ -398,17 +402,17 @@ int orc_neumann_solve(const orc_csr *m, const double *b, uint64_t blen, const or
                     if ((uint64_t)m->col_indices[k] == i) dsum += m->values[k];
                 d = dsum;
             }
-            if (fabs(d) < 1e-14) { rc = ORC_ERR_INVALID_SPARSE_MATRIX; goto done; }
+            if (fabs(d) < 1e-14) { rc = ORC_ERR_INVALID_SPARSE_MATRIX; goto fail; }
             s.dinv[i] = 1.0 / d;
         } else {
             rc = ORC_ERR_INVALID_SPARSE_MATRIX;
-            goto done;
+            goto fail;
         }
     }
     for (uint64_t i = 0; i < n; i++) s.rhs[i] = b[i] * s.dinv[i]; /* :191-194 */
     s.rhs_norm = orc_l2_norm(s.rhs, n);
     if (opt->initial_guess) {                                       /* :197-206 */
-        if (opt->initial_guess_len != n) { rc = ORC_ERR_DIMENSION_MISMATCH; goto done; }
+        if (opt->initial_guess_len != n) { rc = ORC_ERR_DIMENSION_MISMATCH; goto fail; }
         memcpy(s.solution, opt->initial_guess, n * sizeof(double));
     } else if (opt->mode == ORC_MODE_REF_COMPAT) {
         memcpy(s.solution, s.rhs, n * sizeof(double));              /* x_0 = D^-1 b (F4 quirk) */
@@ -424,11 +428,33 @@ int orc_neumann_solve(const orc_csr *m, const double *b, uint64_t blen, const or
         s.matvec++;
         for (uint64_t i = 0; i < n; i++) s.term[i] = (b[i] - s.temp[i]) * s.dinv[i];
     }
-    s.resid_rhs = (opt->mode == ORC_MODE_REF_COMPAT) ? s.rhs : b;
+    s.resid_rhs = (opt->mode == ORC_MODE_REF_COMPAT) ? s.rhs : s.b;
     s.residual_norm = INFINITY;                                     /* :236 */
     s.tolerance = opt->tolerance;
     s.max_terms = opt->max_terms;
     s.series_tolerance = opt->series_tolerance;
+    *sp = s;
+    return ORC_OK;
+fail:
+    free(s.solution); free(s.rhs); free(s.residual); free(s.dinv); free(s.term); free(s.temp); free(s.b);
+    return rc;
+}
+
+static void state_release(nstate *s) {
+    free(s->solution); free(s->rhs); free(s->residual); free(s->dinv); free(s->term); free(s->temp); free(s->b);
+    memset(s, 0, sizeof(*s));
+}
+
+int orc_neumann_solve(const orc_csr *m, const double *b, uint64_t blen, const orc_options *opt,
+                      orc_result *res) {
+    double t_start = now_s();
+    uint64_t n = m->nrows;
+    nstate s;
+    int rc = state_init(&s, m, b, blen, opt);
+    if (rc != ORC_OK) {
+        res->total_time_ms = (now_s() - t_start) * 1e3;
+        return rc;
+    }
 
     /* NeumannSolver::solve (src/solver/neumann.rs:469-555) */
     uint64_t iterations = 0;
@@ -457,10 +483,94 @@ int orc_neumann_solve(const orc_csr *m, const double *b, uint64_t blen, const or
     res->has_error_bound = opt->compute_error_bounds ? s.has_bound : 0;
     res->error_bound = s.bound;
     res->last_term_norm = s.term_norm;
-done:
     res->total_time_ms = (now_s() - t_start) * 1e3;
-    free(s.solution); free(s.rhs); free(s.residual); free(s.dinv); free(s.term); free(s.temp);
+    state_release(&s);
     return rc;
+}
+
+/* ---- the SolverAlgorithm state interface (src/solver/mod.rs:223-252; neumann.rs:350-462) ---- */
+struct orc_state {
+    nstate s;
+    int adaptive_truncation;
+};
+
+/* SolverAlgorithm::initialize (neumann.rs:381-388) */
+int orc_state_new(const orc_csr *m, const double *b, uint64_t blen, const orc_options *opt, orc_state **out) {
+    orc_state *st = (orc_state *)calloc(1, sizeof(orc_state));
+    if (!st) return ORC_ERR_MEMORY_ALLOCATION;
+    int rc = state_init(&st->s, m, b, blen, opt);
+    if (rc != ORC_OK) { free(st); return rc; }
+    st->adaptive_truncation = opt->adaptive_truncation;
+    *out = st;
+    return ORC_OK;
+}
+
+/* SolverAlgorithm::step as the reference intends it (the body it left commented out for lack of a matrix
+ * reference, neumann.rs:404-418): next term, residual, error bounds; Converged (1) once the series converged or
+ * max_terms is reached, else Continue (0). */
+int orc_state_step(orc_state *st, int *step_result) {
+    compute_next_term(&st->s);
+    update_residual(&st->s);
+    if (st->adaptive_truncation) estimate_error_bounds(&st->s);
+    *step_result = (st->s.series_converged || st->s.terms >= st->s.max_terms) ? 1 : 0;
+    return isfinite(st->s.residual_norm) ? ORC_OK : ORC_ERR_NUMERICAL_INSTABILITY;
+}
+
+int orc_state_is_converged(const orc_state *st) { return is_converged(&st->s); }
+
+void orc_state_solution(const orc_state *st, double *x) { memcpy(x, st->s.solution, st->s.n * sizeof(double)); }
+
+/* SolverAlgorithm::update_rhs (neumann.rs:436-462). ref_compat: the literal code (scaled delta added to rhs AND to
+ * the solution, series restarted from the whole new rhs). correct mode: the incremental solve the comment at
+ * :451-453 asks for — b and rhs take the delta, the series restarts from t = D^-1 delta_b only, so the following steps
+ * add A^-1 delta_b to the solution already held. */
+int orc_state_update_rhs(orc_state *st, const uint64_t *idx, const double *delta, uint64_t count) {
+    nstate *s = &st->s;
+    for (uint64_t k = 0; k < count; k++)
+        if (idx[k] >= s->n) return ORC_ERR_INDEX_OUT_OF_BOUNDS;  /* :439-445 (checked up front: no partial update) */
+    if (s->mode == ORC_MODE_CORRECT) memset(s->term, 0, s->n * sizeof(double));
+    for (uint64_t k = 0; k < count; k++) {
+        double scaled = delta[k] * s->dinv[idx[k]];               /* :448 */
+        s->rhs[idx[k]] += scaled;                                 /* :449 */
+        s->b[idx[k]] += delta[k];
+        if (s->mode == ORC_MODE_CORRECT) s->term[idx[k]] += scaled;
+        else s->solution[idx[k]] += scaled;                       /* :453 */
+    }
+    if (s->mode != ORC_MODE_CORRECT) memcpy(s->term, s->rhs, s->n * sizeof(double)); /* :457 */
+    s->terms = 0;                                                 /* :458 */
+    s->series_converged = 0;                                      /* :459 */
+    s->rhs_norm = orc_l2_norm(s->rhs, s->n);
+    return ORC_OK;
+}
+
+/* SolverState::reset (neumann.rs:367-378) */
+void orc_state_reset(orc_state *st) {
+    nstate *s = &st->s;
+    memset(s->solution, 0, s->n * sizeof(double));
+    memset(s->residual, 0, s->n * sizeof(double));
+    s->residual_norm = INFINITY;
+    memcpy(s->term, s->rhs, s->n * sizeof(double));
+    s->terms = 0;
+    s->matvec = 0;
+    s->series_converged = 0;
+    s->has_bound = 0;
+}
+
+void orc_state_info(const orc_state *st, double *residual_norm, uint64_t *matvec_count, uint64_t *terms_computed,
+                    int *series_converged, double *term_norm, int *has_bound, double *bound) {
+    if (residual_norm) *residual_norm = st->s.residual_norm;
+    if (matvec_count) *matvec_count = st->s.matvec;
+    if (terms_computed) *terms_computed = st->s.terms;
+    if (series_converged) *series_converged = st->s.series_converged;
+    if (term_norm) *term_norm = st->s.term_norm;
+    if (has_bound) *has_bound = st->s.has_bound;
+    if (bound) *bound = st->s.bound;
+}
+
+void orc_state_free(orc_state *st) {
+    if (!st) return;
+    state_release(&st->s);
+    free(st);
 }
 
 /* The bare push recurrence (neumann.rs:280-299 + :264-266 + :271) for `nterms` terms after term 0,

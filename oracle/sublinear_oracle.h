@@ -131,6 +131,23 @@ typedef struct {
 int orc_neumann_solve(const orc_csr *m, const double *b, uint64_t blen, const orc_options *opt,
                       orc_result *res);
 
+/* ---- the SolverAlgorithm state interface: initialize / step / is_converged / extract_solution / update_rhs
+ * (src/solver/mod.rs:223-252) and SolverState::reset (neumann.rs:367-378). `m` must outlive the state. ---- */
+typedef struct orc_state orc_state;
+int orc_state_new(const orc_csr *m, const double *b, uint64_t blen, const orc_options *opt, orc_state **out);
+/* step as the reference intends it (the body commented out at neumann.rs:404-418): *step_result 0 = Continue,
+ * 1 = Converged. */
+int orc_state_step(orc_state *st, int *step_result);
+int orc_state_is_converged(const orc_state *st);
+void orc_state_solution(const orc_state *st, double *x);
+/* update_rhs (neumann.rs:436-462): literal in ORC_MODE_REF_COMPAT; in ORC_MODE_CORRECT the series restarts from
+ * D^-1 delta_b so that further steps add A^-1 delta_b to the solution held. */
+int orc_state_update_rhs(orc_state *st, const uint64_t *idx, const double *delta, uint64_t count);
+void orc_state_reset(orc_state *st);
+void orc_state_info(const orc_state *st, double *residual_norm, uint64_t *matvec_count, uint64_t *terms_computed,
+                    int *series_converged, double *term_norm, int *has_bound, double *bound);
+void orc_state_free(orc_state *st);
+
 /* Run exactly `nterms` push iterations t <- t - dinv.(A t); x += t from t = c, x = c (no control
  * flow) and return wall seconds: used as the timed CPU baseline and for per-term parity. */
 double orc_push_iterations(const orc_csr *m, const double *b, uint64_t nterms, int spmv_variant,

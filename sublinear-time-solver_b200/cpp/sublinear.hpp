@@ -5,6 +5,8 @@
 //   sublinear::SolverOptions  <-> SolverOptions (src/solver/mod.rs:22-116)
 //   sublinear::SolverResult   <-> SolverResult  (src/solver/mod.rs:121-195)
 //   sublinear::SolverError    <-> SolverError   (src/error.rs:16-138), thrown where Rust returns Err(..)
+//   sublinear::OptimizedSparseMatrix / OptimizedConjugateGradientSolver / OptimizedSolverConfig / OptimizedSolverResult
+//                             <-> src/optimized_solver.rs:16-340 (the CG consumer of the same SpMV kernel)
 // Header only; link against libsublinear_b200.so. The Rust toolchain is not available in the build image, so this is
 // the compiled-language host layer (the Rust shim in ../rust/ is the same mapping, shipped unbuilt).
 #pragma once
@@ -219,6 +221,86 @@ public:
 private:
     explicit NeumannSolver(sb200_solver *h) : h_(h) {}
     sb200_solver *h_ = nullptr;
+};
+
+// ---- conjugate gradient on the same SpMV kernel (src/optimized_solver.rs) ---------------------------------------
+
+// OptimizedSparseMatrix (src/optimized_solver.rs:16-107): CSR store + matvec / byte counters
+class OptimizedSparseMatrix {
+public:
+    // from_triplets(Vec<(usize,usize,f64)>, rows, cols) -> Result<Self, String> (:40-56)
+    static OptimizedSparseMatrix from_triplets(const std::vector<std::tuple<size_t, size_t, Precision>> &t, size_t rows,
+                                               size_t cols) {
+        return OptimizedSparseMatrix(SparseMatrix::from_triplets(t, rows, cols));
+    }
+    std::pair<size_t, size_t> dimensions() const { return {m_.rows(), m_.cols()}; }  // :59-61
+    size_t nnz() const { return m_.nnz(); }                                         // :64-66
+    // multiply_vector(&self, x, y) (:69-91): asserts the lengths, bumps matvec_count and bytes_processed
+    void multiply_vector(const std::vector<Precision> &x, std::vector<Precision> &y) const {
+        if (x.size() != m_.cols() || y.size() != m_.rows()) throw SolverError(SB200_ERR_DIMENSION_MISMATCH, "assert_eq!(x.len(), cols)");
+        matvec_count_ += 1;
+        bytes_processed_ += m_.nnz() * 8 + x.size() * 8 + y.size() * 8;  // :74
+        m_.multiply_vector(x, y);
+    }
+    std::pair<size_t, size_t> get_performance_stats() const { return {matvec_count_, bytes_processed_}; }  // :94-99
+    void reset_stats() const { matvec_count_ = 0; bytes_processed_ = 0; }                                 // :102-105
+    const SparseMatrix &inner() const { return m_; }
+
+private:
+    explicit OptimizedSparseMatrix(SparseMatrix m) : m_(std::move(m)) {}
+    SparseMatrix m_;
+    mutable size_t matvec_count_ = 0, bytes_processed_ = 0;
+};
+
+struct OptimizedSolverConfig {  // :108-127
+    size_t max_iterations = 1000;
+    Precision tolerance = 1e-6;
+    bool enable_profiling = false;
+};
+
+struct OptimizedSolverStats {  // :150-166
+    size_t matvec_count = 0, dot_product_count = 0, axpy_count = 0, total_flops = 0;
+    double average_bandwidth_gbs = 0.0, average_gflops = 0.0;
+};
+
+struct OptimizedSolverResult {  // :130-147
+    std::vector<Precision> solution;
+    Precision residual_norm = 0.0;
+    size_t iterations = 0;
+    bool converged = false;
+    double computation_time_ms = 0.0;
+    OptimizedSolverStats performance_stats;
+    const std::vector<Precision> &data() const { return solution; }  // :336-340
+};
+
+class OptimizedConjugateGradientSolver {
+public:
+    explicit OptimizedConjugateGradientSolver(OptimizedSolverConfig config = {}) : config_(config) {}
+    static OptimizedConjugateGradientSolver new_(OptimizedSolverConfig config) { return OptimizedConjugateGradientSolver(config); }
+
+    // solve(&mut self, matrix, b) -> Result<OptimizedSolverResult, String> (:182-295); Err(String) -> SolverError
+    OptimizedSolverResult solve(const OptimizedSparseMatrix &matrix, const std::vector<Precision> &b) {
+        sb200_cg_config c;
+        sb200_cg_config_default(&c);
+        c.max_iterations = config_.max_iterations;
+        c.tolerance = config_.tolerance;
+        c.enable_profiling = config_.enable_profiling;
+        sb200_cg_result r;
+        OptimizedSolverResult out;
+        out.solution.resize(b.size());
+        detail::check(sb200_cg_solve_into(matrix.inner().handle(), b.data(), b.size(), &c, out.solution.data(), &r));
+        out.residual_norm = r.residual_norm; out.iterations = r.iterations; out.converged = r.converged;
+        out.computation_time_ms = r.computation_time_ms;
+        out.performance_stats = {size_t(r.matvec_count), size_t(r.dot_product_count), size_t(r.axpy_count),
+                                 size_t(r.total_flops), r.average_bandwidth_gbs, r.average_gflops};
+        stats_ = out.performance_stats;
+        return out;
+    }
+    size_t get_last_iteration_count() const { return stats_.matvec_count; }  // :323-325 (returns matvec_count)
+
+private:
+    OptimizedSolverConfig config_;
+    OptimizedSolverStats stats_;
 };
 
 }  // namespace sublinear

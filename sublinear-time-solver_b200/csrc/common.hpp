@@ -143,6 +143,10 @@ struct TileKernelArgs {
     const TileDesc *tiles;
     uint32_t ntiles;
     uint32_t nrows;
+    // the same matrix in SELL-32 slabs (kernels.cu "the SELL-32 kernel"); sell_ptr == null: CSR kernels only
+    const uint32_t *sell_ptr;   // nblocks + 1 slab offsets (slab = 32 slots, one per row of the block)
+    const uint32_t *sell_cols;
+    const double *sell_vals;
     // vectors
     const double *xin;    // gather source (term / solution / x)
     const double *xin_own; // value of xin for local row i is xin_own[i] (== xin + row_base)
@@ -164,7 +168,6 @@ struct TileKernelArgs {
     double *norm_log;     // optional: norm_log[it] = ||t_it||^2 (bare recurrence)
     unsigned long long *phase_log;  // debug ($SUBLINEAR_B200_PHASE_LOG=1): per-phase cycles of thread 0, summed over CTAs
     PeerExchange px;      // row-partitioned P2P exchange (warp-stream kernel only)
-    int probe;            // measurement aid ($SUBLINEAR_B200_WARP_PROBE): 0 = the real kernel
 };
 
 // launchers (kernels.cu). grid = 0 -> persistent grid sized from occupancy.
@@ -180,6 +183,8 @@ struct SetupOut {
 };
 int32_t launch_setup_rows(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
                           uint32_t row_base, int compat_diag, SetupOut out, cudaStream_t stream);
+int32_t launch_csr_to_sell(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
+                           const uint32_t *sell_ptr, uint32_t *sell_cols, double *sell_vals, cudaStream_t stream);
 int32_t launch_col_dominance(const double *col_diag, const double *col_off, uint32_t n, unsigned long long *first_bad,
                              cudaStream_t stream);
 // iteration 0 (neumann.rs:191-211 + first compute_next_term): c = b*dinv; t = c (or (b - Ax0)*dinv); x = base + t
@@ -204,6 +209,10 @@ struct InitArgs {
 int32_t launch_init_state(const InitArgs &a, cudaStream_t stream);
 int init_state_grid();
 int32_t launch_scale(double *v, uint64_t n, double factor, cudaStream_t stream);
+// SolverAlgorithm state interface (state.cu): op 0 = accumulate term 0 (x += t, ||t||^2 as a term), op 1 = ||t||^2 -> red[0]
+int32_t launch_state_vec(int op, const double *t, double *x, uint64_t n, LoopCtl *ctl, double *partials, cudaStream_t stream);
+int32_t launch_update_rhs(const uint64_t *idx, const double *delta, uint64_t count, const double *dinv, double *b,
+                          double *rhs, double *also, cudaStream_t stream);
 // distributed: finish the loop logic after the partial norms were all-reduced (kind: 1 = term, 2 = residual)
 int32_t launch_dist_tail(LoopCtl *ctl, int kind, uint32_t it, int last_in_iter, int identity_res, int force,
                          double *norm_log, cudaStream_t stream);

@@ -645,7 +645,10 @@ static int32_t launch_any(int cfg, Epilogue epi, const TileKernelArgs &a, cudaSt
 
 static int32_t launch_warp_any(Epilogue epi, const TileKernelArgs &a, cudaStream_t stream, int *mg);
 
+static int32_t launch_sell_any(Epilogue epi, const TileKernelArgs &a, cudaStream_t stream, int *mg);
+
 int32_t launch_tile_kernel(int cfg, Epilogue epi, const TileKernelArgs &a, cudaStream_t stream) {
+    if (cfg < 0 && a.sell_ptr != nullptr) return launch_sell_any(epi, a, stream, nullptr);
     if (cfg < 0) return launch_warp_any(epi, a, stream, nullptr);
     if (epi == EPI_CG) return fail(SB200_ERR_INVALID_INPUT, "the CG epilogue exists in the warp-stream kernel only");
     if (reinterpret_cast<uintptr_t>(a.xin) & 15u)  // 16-byte gathers and the TMA window copy
@@ -653,11 +656,15 @@ int32_t launch_tile_kernel(int cfg, Epilogue epi, const TileKernelArgs &a, cudaS
     return launch_any(cfg, epi, a, stream, nullptr);
 }
 
+// upper bound of the number of partial sums a launch of this configuration writes (callers size `partials` from it)
 int tile_kernel_max_grid(int cfg, Epilogue epi) {
     int mg = 0;
     TileKernelArgs dummy{};
-    if ((cfg < 0 ? launch_warp_any(epi, dummy, nullptr, &mg) : launch_any(cfg, epi, dummy, nullptr, &mg)) != SB200_OK) return 0;
-    return mg;
+    if (cfg >= 0) return launch_any(cfg, epi, dummy, nullptr, &mg) == SB200_OK ? mg : 0;
+    int ms = 0;
+    if (launch_warp_any(epi, dummy, nullptr, &mg) != SB200_OK) return 0;
+    if (launch_sell_any(epi, dummy, nullptr, &ms) != SB200_OK) return 0;  // one partial per warp
+    return mg > ms ? mg : ms;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -766,41 +773,7 @@ __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
                 double p[EPL];
 #pragma unroll
                 for (int q = 0; q < EPL; q++) p[q] = 0.0;
-                if (e < b1 && (a.probe & 7) != 0) {
-                    // measurement aid ($SUBLINEAR_B200_WARP_PROBE, results are NOT the SpMV): isolates the cost of the
-                    // three phases of a chunk. 1: stream only (no gathers), 2: gathers only (hashed columns, no
-                    // stream), 3: stream + gathers (as 0; the caller also skips the ordered row sums)
-                    uint32_t cx[EPL];
-                    double v[EPL];
-                    if ((a.probe & 7) == 2) {
-#pragma unroll
-                        for (int q = 0; q < EPL; q++) {
-                            uint32_t h = (e + q) * 0x9E3779B9u;
-                            h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
-                            cx[q] = (uint32_t)(h % a.xin_len);
-                            v[q] = 1.0;
-                        }
-                    } else {
-                        if constexpr (EPL == 4) {
-                            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                                         : "=r"(cx[0]), "=r"(cx[1]), "=r"(cx[2]), "=r"(cx[3])
-                                         : "l"(a.cols + e), "l"(pol_stream));
-                        } else {
-                            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-                                         : "=r"(cx[0]), "=r"(cx[1]), "=r"(cx[2]), "=r"(cx[3]), "=r"(cx[EPL - 4]), "=r"(cx[EPL - 3]),
-                                           "=r"(cx[EPL - 2]), "=r"(cx[EPL - 1])
-                                         : "l"(a.cols + e), "l"(pol_stream));
-                        }
-#pragma unroll
-                        for (int q = 0; q < EPL; q += 4)
-                            asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;"
-                                         : "=d"(v[q]), "=d"(v[q + 1]), "=d"(v[q + 2]), "=d"(v[q + 3])
-                                         : "l"(a.vals + e + q), "l"(pol_stream));
-                    }
-#pragma unroll
-                    for (int q = 0; q < EPL; q++)
-                        p[q] = v[q] * ((a.probe & 7) == 1 ? (double)(cx[q] & 1u) : ld_gather(a.xin + cx[q], pol_gather));
-                } else if (e < b1) {
+                if (e < b1) {
                     uint32_t cx[EPL];
                     double v[EPL];
                     // 256-bit loads (SASS LDG.E.256): the warp reads its slice of `values` contiguously and every
@@ -829,11 +802,6 @@ __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
                     for (int q = 0; q < EPL; q++) xg[q] = ld_gather(a.xin + cx[q], pol_gather);
 #pragma unroll
                     for (int q = 0; q < EPL; q++) p[q] = v[q] * xg[q];
-                }
-                if ((a.probe & 7) == 3) {  // measurement aid: no shared-memory pass, no ordered sums
-#pragma unroll
-                    for (int q = 0; q < EPL; q++) acc += p[q];
-                    continue;
                 }
 #pragma unroll
                 for (int q = 0; q < EPL; q += 2)
@@ -890,10 +858,7 @@ static int32_t launch_warp_one(const TileKernelArgs &a, cudaStream_t stream, int
     unsigned need = (nblocks + NT / 32 - 1) / (NT / 32);
     unsigned grid = need < (unsigned)max_grid[dev] ? need : (unsigned)max_grid[dev];
     if (grid == 0) grid = 1;
-    static int probe = [] { const char *e = getenv("SUBLINEAR_B200_WARP_PROBE"); return e ? atoi(e) : 0; }();
-    TileKernelArgs ap = a;
-    ap.probe = probe;
-    warp_kernel<EPI, NT, EPL><<<grid, NT, 0, stream>>>(ap);
+    warp_kernel<EPI, NT, EPL><<<grid, NT, 0, stream>>>(a);
     SB_CUDA(cudaGetLastError());
     return SB200_OK;
 }
@@ -915,6 +880,225 @@ static int32_t launch_warp_any(Epilogue epi, const TileKernelArgs &a, cudaStream
         case EPI_CG: return launch_warp_one<EPI_CG, 256, 4>(a, stream, mg);
         default: return launch_warp_one<EPI_RESID, 256, 4>(a, stream, mg);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the SELL-32 kernel (default whenever the padded layout costs <= 25 % extra slots, see matrix.cu)
+// ---------------------------------------------------------------------------------------------------------
+// Measured on the warp-stream kernel (profiles/r1_warp_probe_phases.log): on uniform-random columns the x[col] gathers
+// alone cost 687 us of the 808 us launch although the same gathers run at 265-287 G/s (350-377 us) in isolation. The
+// difference is the L1: every in-flight gather holds a 128-byte L1 line, the line count is what shared memory leaves
+// of the 256 KB array, and the driver sizes the carve-out for the maximum number of resident CTAs — 64 KB for the
+// warp-stream kernel's 9 KB of product staging per CTA (bench/gather_probe.cu: 267 / 223 / 176-212 / 120 / 56 G/s at
+// 256 / 192 / 124 / 60 / 28 KB of L1). This kernel therefore uses NO shared memory at all:
+//   * ingest re-lays the CSR slices out in blocks of 32 consecutive rows, element k of row r at
+//     sell_ptr[blk]*32 + k*32 + r (sliced ELLPACK, slice height 32 = one warp; zero-padded to the longest row of the
+//     block), so lane r reads ITS OWN row's k-th column index / value with fully coalesced 128 / 256-byte warp loads —
+//     no transposition through shared memory, no shuffles;
+//   * lane r accumulates row r left to right in registers: the reference's order (sparse.rs:193-203), bit for bit;
+//   * U stream loads, then U gathers are in flight per lane before the first add;
+//   * the norm reduction goes warp shuffle -> one partial per warp in global memory -> fixed-order sum by one warp of
+//     the last CTA (elected with __syncthreads_or, no shared flag).
+// Padding slots hold value 0 / column 0 and are never gathered or added (k < row length), so non-finite x entries
+// cannot leak into other rows.
+__device__ __forceinline__ uint32_t ld_stream_u32_hint(const uint32_t *p, uint64_t policy) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ double ld_stream_f64_hint(const double *p, uint64_t policy) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+    return v;
+}
+
+// warp partial -> global partial array -> warp 0 of the last CTA sums all partials in index order. No shared memory.
+template <int NT>
+__device__ __forceinline__ void grid_reduce_and_tail_regs(double sq, double aux, LoopCtl *ctl, double *partials, int kind,
+                                                          uint32_t it, int last_in_iter, int identity_res, int defer,
+                                                          double *norm_log, const PeerExchange *px) {
+    constexpr int WARPS = NT / 32;
+    const bool p2p = px != nullptr && px->world > 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned nparts = gridDim.x * WARPS;
+    if (p2p) __threadfence_system();  // this thread's stores into peer memory, before the CTA reports in
+    sq = warp_sum(sq);
+    if (identity_res) aux = warp_sum(aux);
+    if (lane == 0) {
+        partials[blockIdx.x * WARPS + warp] = sq;
+        if (identity_res) partials[nparts + blockIdx.x * WARPS + warp] = aux;
+        if (p2p) __threadfence_system(); else __threadfence();
+    }
+    __syncthreads();
+    int last = 0;
+    if (threadIdx.x == 0) last = atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1;
+    last = __syncthreads_or(last);
+    if (last && warp == 0) {
+        __threadfence();
+        double s = 0.0, a2 = 0.0;
+        for (unsigned i = lane; i < nparts; i += 32) s += __ldcg(partials + i);
+        if (identity_res)
+            for (unsigned i = lane; i < nparts; i += 32) a2 += __ldcg(partials + nparts + i);
+        s = warp_sum(s);
+        if (identity_res) a2 = warp_sum(a2);
+        if (lane == 0) {
+            ctl->ticket = 0;
+            if (p2p) {
+                __threadfence_system();
+                peer_signal(ctl, *px, s, a2);  // the wait kernel that follows runs tail_logic on the global sums
+            } else {
+                tail_logic(ctl, kind, s, a2, it, last_in_iter, identity_res, defer, norm_log);
+            }
+        }
+    }
+}
+
+template <int EPI, int NT, int U>
+__global__ void __launch_bounds__(NT) sell_kernel(const TileKernelArgs a) {
+    constexpr int WARPS = NT / 32;
+    if (EPI != EPI_SPMV) {
+        if (!a.force && a.ctl->alive == 0) return;  // loop already finished: no-op launch
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t pol_stream = policy_evict_first();
+    const uint64_t pol_gather = policy_evict_last();
+    const uint32_t nrows = a.nrows;
+    const uint32_t nblocks = (nrows + 31u) >> 5;
+    const uint32_t nwarps = gridDim.x * WARPS;
+
+    double sq = 0.0, aux = 0.0;
+    for (uint32_t blk = blockIdx.x * WARPS + warp; blk < nblocks; blk += nwarps) {
+        const uint32_t row = (blk << 5) + lane;
+        const bool active = row < nrows;
+        uint32_t len = 0;
+        if (active) len = a.row_ptr[row + 1u] - a.row_ptr[row];
+        const uint32_t off = a.sell_ptr[blk];           // warp-uniform: first 32-slot slab of the block
+        const uint32_t width = a.sell_ptr[blk + 1u] - off;  // slabs = longest row of the block
+        double own = 0.0, dv = 0.0, xs = 0.0, rh = 0.0;
+        if (active) row_operands<EPI>(a, row, own, dv, xs, rh);
+        double acc = (EPI == EPI_SPMV && a.accumulate) ? xs : 0.0;
+        const size_t base = (size_t)off * 32u + (size_t)lane;
+        const uint32_t *__restrict__ cp = a.sell_cols + base;
+        const double *__restrict__ vp = a.sell_vals + base;
+        for (uint32_t k0 = 0; k0 < width; k0 += U) {
+            uint32_t c[U];
+            double v[U], x[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                c[u] = 0u;
+                v[u] = 0.0;
+                if (k0 + u < width) {  // warp-uniform
+                    c[u] = ld_stream_u32_hint(cp + (size_t)(k0 + u) * 32u, pol_stream);
+                    v[u] = ld_stream_f64_hint(vp + (size_t)(k0 + u) * 32u, pol_stream);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                x[u] = 0.0;
+                if (k0 + u < len) x[u] = ld_gather(a.xin + c[u], pol_gather);
+            }
+            // left-to-right accumulation, the order of CSRStorage::multiply_vector_add (sparse.rs:193-203)
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (k0 + u < len) acc += v[u] * x[u];
+        }
+        if (active) row_epilogue<EPI>(a, row, acc, own, dv, xs, rh, sq, aux);
+    }
+    if (EPI != EPI_SPMV) {
+        const int kind = EPI == EPI_PUSH ? TAIL_TERM : (EPI == EPI_CG ? TAIL_CG_PAP : TAIL_RESID);
+        grid_reduce_and_tail_regs<NT>(sq, aux, a.ctl, a.partials, kind, a.it, a.last_in_iter, a.identity_res, a.defer_tail,
+                                      a.norm_log, &a.px);
+    }
+}
+
+constexpr int kSellThreads = 256;
+
+template <int EPI, int U>
+static int32_t launch_sell_one(const TileKernelArgs &a, cudaStream_t stream, int *max_grid_out) {
+    static int max_grid[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 16) return fail(SB200_ERR_ALGORITHM, "device index %d out of range", dev);
+    if (max_grid[dev] == 0) {
+        // no shared memory: ask for the smallest carve-out so the whole 256 KB array serves as L1
+        SB_CUDA(cudaFuncSetAttribute(sell_kernel<EPI, kSellThreads, U>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxL1));
+        int per_sm = 0, sms = 0;
+        SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sell_kernel<EPI, kSellThreads, U>, kSellThreads, 0));
+        SB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (per_sm < 1) return fail(SB200_ERR_ALGORITHM, "SELL kernel does not fit on an SM");
+        static int cap = [] { const char *e = getenv("SUBLINEAR_B200_SELL_CTAS"); return e ? atoi(e) : 0; }();
+        if (cap > 0 && per_sm > cap) per_sm = cap;
+        max_grid[dev] = per_sm * sms;  // persistent grid: a whole number of CTAs per SM (148 SMs on B200)
+    }
+    if (max_grid_out) {
+        *max_grid_out = max_grid[dev] * (kSellThreads / 32);  // one partial per WARP (callers size `partials` from this)
+        return SB200_OK;
+    }
+    if (a.nrows == 0 && EPI == EPI_SPMV) return SB200_OK;
+    const uint32_t nblocks = (a.nrows + 31u) / 32u;
+    unsigned need = (nblocks + kSellThreads / 32 - 1) / (kSellThreads / 32);
+    unsigned grid = need < (unsigned)max_grid[dev] ? need : (unsigned)max_grid[dev];
+    if (grid == 0) grid = 1;
+    sell_kernel<EPI, kSellThreads, U><<<grid, kSellThreads, 0, stream>>>(a);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+template <int U>
+static int32_t launch_sell_u(Epilogue epi, const TileKernelArgs &a, cudaStream_t stream, int *mg) {
+    switch (epi) {
+        case EPI_SPMV: return launch_sell_one<EPI_SPMV, U>(a, stream, mg);
+        case EPI_PUSH: return launch_sell_one<EPI_PUSH, U>(a, stream, mg);
+        case EPI_CG: return launch_sell_one<EPI_CG, U>(a, stream, mg);
+        default: return launch_sell_one<EPI_RESID, U>(a, stream, mg);
+    }
+}
+
+static int32_t launch_sell_any(Epilogue epi, const TileKernelArgs &a, cudaStream_t stream, int *mg) {
+    // stream loads / gathers in flight per lane ($SUBLINEAR_B200_SELL_U; measurement aid, same results bit for bit)
+    static int u = [] { const char *e = getenv("SUBLINEAR_B200_SELL_U"); return e ? atoi(e) : 0; }();
+    switch (u) {
+        case 4: return launch_sell_u<4>(epi, a, stream, mg);
+        case 5: return launch_sell_u<5>(epi, a, stream, mg);
+        case 10: return launch_sell_u<10>(epi, a, stream, mg);
+        default: return launch_sell_u<8>(epi, a, stream, mg);
+    }
+}
+
+// one-off layout pass at ingest: CSR slices -> SELL-32 slabs (warp per block of 32 rows)
+__global__ void csr_to_sell_kernel(const double *__restrict__ vals, const uint32_t *__restrict__ cols,
+                                   const uint32_t *__restrict__ row_ptr, uint32_t nrows,
+                                   const uint32_t *__restrict__ sell_ptr, uint32_t *__restrict__ sc,
+                                   double *__restrict__ sv) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t nblocks = (nrows + 31u) >> 5;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < nblocks; blk += nwarps) {
+        const uint32_t row = (blk << 5) + lane;
+        uint32_t rs = 0, len = 0;
+        if (row < nrows) {
+            rs = row_ptr[row];
+            len = row_ptr[row + 1u] - rs;
+        }
+        const uint32_t off = sell_ptr[blk], width = sell_ptr[blk + 1u] - off;
+        for (uint32_t k = 0; k < width; k++) {
+            const size_t idx = ((size_t)off + k) * 32u + (size_t)lane;
+            sc[idx] = k < len ? cols[rs + k] : 0u;
+            sv[idx] = k < len ? vals[rs + k] : 0.0;
+        }
+    }
+}
+
+int32_t launch_csr_to_sell(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
+                           const uint32_t *sell_ptr, uint32_t *sell_cols, double *sell_vals, cudaStream_t stream) {
+    if (nrows == 0) return SB200_OK;
+    const uint32_t nblocks = (nrows + 31u) / 32u;
+    unsigned grid = (nblocks + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    csr_to_sell_kernel<<<grid, 256, 0, stream>>>(vals, cols, row_ptr, nrows, sell_ptr, sell_cols, sell_vals);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1051,6 +1235,57 @@ int32_t launch_init_state(const InitArgs &a, cudaStream_t stream) {
     if (grid > (unsigned)init_state_grid()) grid = init_state_grid();
     if (grid == 0) grid = 1;
     init_state_kernel<<<grid, kInitThreads, 0, stream>>>(a);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small vector passes of the SolverAlgorithm state interface (csrc/state.cu)
+// ---------------------------------------------------------------------------------------------------------
+// op 0: term 0 of compute_next_term (neumann.rs:264-271 with terms_computed == 0): x += t, ||t||^2 -> TAIL_TERM(it = 0)
+// op 1: ||v||^2 -> ctl->red[0] (utils::l2_norm, solver/mod.rs:369-371)
+__global__ void __launch_bounds__(kInitThreads) state_vec_kernel(int op, const double *__restrict__ t, double *x, uint64_t n,
+                                                                 LoopCtl *ctl, double *partials) {
+    __shared__ double s_red[kInitThreads / 32];
+    __shared__ int s_flag;
+    double sq = 0.0;
+    for (uint64_t i = blockIdx.x * (uint64_t)kInitThreads + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kInitThreads) {
+        const double ti = t[i];
+        if (op == 0) x[i] = x[i] + ti;
+        sq += ti * ti;
+    }
+    grid_reduce_and_tail<kInitThreads>(sq, 0.0, ctl, partials, op == 0 ? TAIL_TERM : TAIL_NONE, 0u, 0, 0, op == 1, nullptr,
+                                       s_red, &s_flag);
+}
+
+int32_t launch_state_vec(int op, const double *t, double *x, uint64_t n, LoopCtl *ctl, double *partials,
+                         cudaStream_t stream) {
+    uint64_t g = (n + kInitThreads - 1) / kInitThreads;
+    unsigned grid = g > (uint64_t)init_state_grid() ? (unsigned)init_state_grid() : (unsigned)(g ? g : 1);
+    state_vec_kernel<<<grid, kInitThreads, 0, stream>>>(op, t, x, n, ctl, partials);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+// update_rhs (neumann.rs:436-462): the (index, delta) pairs are applied IN ORDER by one thread — the reference's loop
+// is sequential and an index may repeat; the lists are small by nature (an incremental update). b += delta,
+// rhs += delta * dinv; `also` (the solution in ref_compat, the restarted term in correct mode) takes the scaled delta too.
+__global__ void update_rhs_kernel(const uint64_t *__restrict__ idx, const double *__restrict__ delta, uint64_t count,
+                                  const double *__restrict__ dinv, double *b, double *rhs, double *also) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (uint64_t k = 0; k < count; k++) {
+        const uint64_t i = idx[k];
+        const double scaled = delta[k] * dinv[i];  // :448
+        rhs[i] += scaled;                          // :449
+        b[i] += delta[k];
+        also[i] += scaled;                         // :453 (solution) / restarted term
+    }
+}
+
+int32_t launch_update_rhs(const uint64_t *idx, const double *delta, uint64_t count, const double *dinv, double *b,
+                          double *rhs, double *also, cudaStream_t stream) {
+    if (count == 0) return SB200_OK;
+    update_rhs_kernel<<<1, 32, 0, stream>>>(idx, delta, count, dinv, b, rhs, also);
     SB_CUDA(cudaGetLastError());
     return SB200_OK;
 }

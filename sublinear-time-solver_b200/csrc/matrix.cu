@@ -18,6 +18,9 @@ sb200_matrix::~sb200_matrix() {
     d_cols.release();
     d_row_ptr.release();
     d_tiles.release();
+    d_sell_ptr.release();
+    d_sell_cols.release();
+    d_sell_vals.release();
     d_dinv[0].release();
     d_dinv[1].release();
     if (stream) cudaStreamDestroy(stream);
@@ -57,6 +60,14 @@ uint64_t Workspace::bytes() const {
     return 8ull * (x.n + c.n + b.n + tmp.n + t[0].n + t[1].n + partials.n + norm_log.n) + sizeof(LoopCtl);
 }
 
+void matrix_retain(sb200_matrix *m) {
+    if (m) m->refcount.fetch_add(1, std::memory_order_relaxed);
+}
+
+void matrix_release(sb200_matrix *m) {
+    if (m && m->refcount.fetch_sub(1, std::memory_order_acq_rel) == 1) delete m;
+}
+
 std::unique_ptr<Workspace> matrix_acquire_ws(sb200_matrix *m) {
     std::lock_guard<std::mutex> lk(m->mu);
     if (!m->pool.empty()) {
@@ -87,6 +98,43 @@ static void build_tiles(const uint32_t *row_ptr, uint64_t nrows, TileCfg cfg, st
         r = r1;
     }
     tiles.push_back(TileDesc{(uint32_t)nrows, row_ptr[nrows]});
+}
+
+// SELL-32 copy for the hot kernels: per block of 32 rows `width` = its longest row, slab offsets by prefix sum on the
+// host (O(n) over the host row_ptr copy), the transposition itself on the device from the uploaded CSR slices.
+// $SUBLINEAR_B200_SELL = 1 / 0 forces / forbids the layout; default: used when it costs <= 25 % extra slots.
+static int32_t build_sell(sb200_matrix *m) {
+    m->use_sell = false;
+    if (m->tile_cfg >= 0 || m->nrows == 0) return SB200_OK;  // TMA tile pipeline selected: CSR only
+    const char *e = getenv("SUBLINEAR_B200_SELL");
+    const int force = e ? atoi(e) : -1;
+    if (force == 0) return SB200_OK;
+    const uint32_t *rp = m->h_row_ptr.data();
+    const uint64_t nrows = m->nrows, nblocks = (nrows + 31) / 32;
+    std::vector<uint32_t> sp(nblocks + 1);
+    uint64_t slabs = 0, max_width = 0;
+    for (uint64_t b = 0; b < nblocks; b++) {
+        sp[b] = (uint32_t)slabs;
+        uint32_t w = 0;
+        const uint64_t r1 = std::min(nrows, b * 32 + 32);
+        for (uint64_t r = b * 32; r < r1; r++) w = std::max(w, rp[r + 1] - rp[r]);
+        slabs += w;
+        max_width = std::max<uint64_t>(max_width, w);
+        if (slabs >= 0xFFFFFFF0ull) return SB200_OK;  // slab offsets are u32: keep the CSR kernels
+    }
+    sp[nblocks] = (uint32_t)slabs;
+    const uint64_t slots = slabs * 32;
+    if (force != 1 && (slots > m->nnz + m->nnz / 4 + 2048 || max_width > 4096)) return SB200_OK;
+    SB_TRY(m->d_sell_ptr.alloc(nblocks + 1));
+    SB_TRY(m->d_sell_cols.alloc(slots));
+    SB_TRY(m->d_sell_vals.alloc(slots));
+    SB_TRY(copy_h2d(m->d_sell_ptr.p, sp.data(), (nblocks + 1) * sizeof(uint32_t), m->stream));
+    SB_TRY(launch_csr_to_sell(m->d_vals.p, m->d_cols.p, m->d_row_ptr.p, (uint32_t)nrows, m->d_sell_ptr.p, m->d_sell_cols.p,
+                              m->d_sell_vals.p, m->stream));
+    SB_CUDA(cudaStreamSynchronize(m->stream));  // `sp` is staged asynchronously
+    m->sell_slabs = slabs;
+    m->use_sell = true;
+    return SB200_OK;
 }
 
 // Upload a validated host CSR. Exactly one of row_ptr64 / row_ptr32 is non-null.
@@ -160,6 +208,7 @@ int32_t matrix_from_host_csr(const uint64_t *row_ptr64, const uint32_t *row_ptr3
     SB_TRY(copy_h2d(m->d_cols.p, cols, nnz * sizeof(uint32_t), m->stream));
     SB_TRY(copy_h2d(m->d_row_ptr.p, rp, (nrows + 1) * sizeof(uint32_t), m->stream));
     SB_TRY(copy_h2d(m->d_tiles.p, tiles.data(), tiles.size() * sizeof(TileDesc), m->stream));
+    SB_TRY(build_sell(m.get()));
     SB_CUDA(cudaStreamSynchronize(m->stream));
     *out = m.release();
     return SB200_OK;
@@ -171,6 +220,9 @@ void fill_tile_args(const sb200_matrix *m, TileKernelArgs &a) {
     a.row_ptr = m->d_row_ptr.p;
     a.tiles = m->d_tiles.p;
     a.ntiles = m->ntiles;
+    a.sell_ptr = m->use_sell ? m->d_sell_ptr.p : nullptr;
+    a.sell_cols = m->d_sell_cols.p;
+    a.sell_vals = m->d_sell_vals.p;
     a.nrows = (uint32_t)m->nrows;
     a.row_base = (uint32_t)m->row_base;
     a.xin_len = m->ncols;
@@ -390,7 +442,9 @@ int32_t sb200_matrix_identity(uint64_t size, sb200_matrix **out) {
     return sb200_matrix_diagonal(d.data(), size, out);
 }
 
-void sb200_matrix_free(sb200_matrix *m) { delete m; }
+// The handle is reference counted: a solver state (csrc/state.cu) shares ownership, so callers (and garbage collectors)
+// may free the matrix handle and its states in any order.
+void sb200_matrix_free(sb200_matrix *m) { sb200::matrix_release(m); }
 
 int32_t sb200_matrix_rows(const sb200_matrix *m, uint64_t *out) {
     if (!m || !out) return fail(SB200_ERR_INVALID_INPUT, "null argument");
@@ -405,6 +459,17 @@ int32_t sb200_matrix_cols(const sb200_matrix *m, uint64_t *out) {
 int32_t sb200_matrix_nnz(const sb200_matrix *m, uint64_t *out) {
     if (!m || !out) return fail(SB200_ERR_INVALID_INPUT, "null argument");
     *out = m->nnz;
+    return SB200_OK;
+}
+
+int32_t sb200_matrix_storage_info(const sb200_matrix *m, int32_t *layout, uint64_t *slots, uint64_t *device_bytes) {
+    if (!m) return fail(SB200_ERR_INVALID_INPUT, "null argument");
+    if (layout) *layout = m->use_sell ? SB200_LAYOUT_SELL32 : SB200_LAYOUT_CSR;
+    if (slots) *slots = m->use_sell ? m->sell_slabs * 32 : m->nnz;
+    if (device_bytes)
+        *device_bytes = m->d_vals.n * 8 + m->d_cols.n * 4 + m->d_row_ptr.n * 4 + m->d_tiles.n * sizeof(TileDesc) +
+                        m->d_sell_ptr.n * 4 + m->d_sell_cols.n * 4 + m->d_sell_vals.n * 8 + m->d_dinv[0].n * 8 +
+                        m->d_dinv[1].n * 8;
     return SB200_OK;
 }
 
@@ -515,6 +580,7 @@ int32_t sb200_matrix_scale(sb200_matrix *m, double factor) {
     if (!m) return fail(SB200_ERR_INVALID_INPUT, "null matrix");
     DeviceGuard g(m->device);
     SB_TRY(launch_scale(m->d_vals.p, m->nnz, factor, m->stream));
+    if (m->use_sell) SB_TRY(launch_scale(m->d_sell_vals.p, m->sell_slabs * 32, factor, m->stream));
     SB_CUDA(cudaStreamSynchronize(m->stream));
     std::lock_guard<std::mutex> lk(m->mu);
     m->analysed[0] = m->analysed[1] = m->col_analysed = false;  // cached D^-1 is stale

@@ -1,6 +1,7 @@
 // matrix.hpp — the device-resident SparseMatrix handle (internal).
 #pragma once
 
+#include <atomic>
 #include <memory>
 
 #include "common.hpp"
@@ -31,6 +32,7 @@ struct Workspace {
 }  // namespace sb200
 
 struct sb200_matrix {
+    std::atomic<int> refcount{1};  // the creator's handle + one per live solver state (matrix_retain / matrix_release)
     int device = 0;
     uint64_t nrows = 0, ncols = 0, nnz = 0;
     int tile_cfg = 0;
@@ -40,6 +42,13 @@ struct sb200_matrix {
     sb200::DevBuf<uint32_t> d_cols;
     sb200::DevBuf<uint32_t> d_row_ptr;
     sb200::DevBuf<sb200::TileDesc> d_tiles;
+    // SELL-32 copy of the same entries for the hot kernels (kernels.cu "the SELL-32 kernel"); empty when the padded
+    // layout would cost more than 25 % extra slots (power-law rows) or a TMA tile configuration is selected
+    sb200::DevBuf<uint32_t> d_sell_ptr;   // nblocks + 1 slab offsets
+    sb200::DevBuf<uint32_t> d_sell_cols;  // sell_slabs * 32
+    sb200::DevBuf<double> d_sell_vals;    // sell_slabs * 32
+    uint64_t sell_slabs = 0;
+    bool use_sell = false;
     cudaStream_t stream = nullptr;  // for host-pointer entry points
 
     // distributed: this handle holds rows [row_base, row_base + nrows) of an n_global-square system
@@ -70,6 +79,8 @@ int32_t matrix_from_host_csr(const uint64_t *row_ptr64, const uint32_t *row_ptr3
                              sb200_matrix **out);
 int32_t matrix_analyse(sb200_matrix *m, int mode, bool need_cols);
 int32_t matrix_spmv_dev(const sb200_matrix *m, const double *x_dev, double *y_dev, int accumulate, cudaStream_t st);
+void matrix_retain(sb200_matrix *m);
+void matrix_release(sb200_matrix *m);  // deletes the handle when the last owner lets go
 std::unique_ptr<Workspace> matrix_acquire_ws(sb200_matrix *m);
 void matrix_release_ws(sb200_matrix *m, std::unique_ptr<Workspace> ws);
 void fill_tile_args(const sb200_matrix *m, TileKernelArgs &a);

@@ -34,7 +34,8 @@ int32_t validate_options(const sb200_options *opt) {
 
 // The solve on device-resident vectors. b_dev: n doubles; x0_dev: initial guess or null; x_out_dev: n doubles.
 int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev, const double *x0_dev,
-                     const sb200_options *opt, double *x_out_dev, cudaStream_t st, Workspace &ws, SolveStats &stats) {
+                     const sb200_options *opt, double *x_out_dev, cudaStream_t st, Workspace &ws, SolveStats &stats,
+                     const StreamHook *hook) {
     const uint64_t n = m->nrows;
     const int cfg = m->tile_cfg;
     const bool compat = opt->mode == SB200_MODE_REF_COMPAT;
@@ -163,7 +164,33 @@ int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev
     // ---- iterations 1 .. : one fused push kernel per term, residual kernel every 5th iteration ----
     uint64_t it = 1;
     const uint64_t push_end = std::min(max_it, max_terms);  // iterations [1, push_end) compute a term
-    const uint64_t kBatch = 8;
+    const bool streaming = hook && hook->fn && hook->interval > 0;
+    const uint64_t kBatch = streaming ? hook->interval : 8;  // the loop state is read back once per batch
+    bool stopped_by_callback = false;
+    // PartialSolution (solver/mod.rs:198-217) after the batch that ended at iteration `upto`
+    auto emit_partial = [&](uint64_t upto) -> int32_t {
+        const LoopCtl &c = *ws.h_ctl;
+        SB_CUDA(cudaMemcpyAsync(hook->host_x, x_out_dev, n * 8, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        sb200_partial_solution p{};
+        p.iteration = std::min<uint64_t>(c.iterations, upto);
+        p.solution = hook->host_x;
+        p.solution_len = n;
+        p.residual_norm = c.res_norm;
+        p.converged = (c.res_norm <= opt->tolerance) || (c.sconv && c.terms < max_terms);
+        const double tn = std::sqrt(c.term_norm2), t0n = std::sqrt(c.rhs_norm2);
+        if (c.terms > 1 && tn > 0.0 && t0n > 0.0 && tn < t0n) {
+            const double rho = std::pow(tn / t0n, 1.0 / (double)(c.terms - 1));  // observed contraction per term
+            if (rho < 1.0 && rho > 0.0) {
+                const double need = tn < s->series_tolerance ? 0.0 : std::ceil(std::log(s->series_tolerance / tn) / std::log(rho));
+                p.has_estimated_remaining = 1;
+                p.estimated_remaining = (uint64_t)std::max(0.0, need);
+            }
+        }
+        p.timestamp_ms = wall_ms() - hook->t0_ms;
+        if (hook->fn(&p, hook->user) != 0) stopped_by_callback = true;
+        return SB200_OK;
+    };
     bool alive = loop_runs && max_terms > 0;
     if (alive) {
         // small systems finish within the first batch; read the state only after real work was queued
@@ -187,6 +214,14 @@ int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev
             }
             SB_TRY(read_ctl());
             alive = ws.h_ctl->alive != 0;
+            if (streaming) {
+                SB_TRY(emit_partial(it));
+                if (stopped_by_callback && alive) {  // freeze the loop where the caller stopped it
+                    ws.h_ctl->alive = 0;
+                    SB_CUDA(cudaMemcpyAsync(ws.ctl.p, ws.h_ctl, sizeof(LoopCtl), cudaMemcpyHostToDevice, st));
+                    alive = false;
+                }
+            }
         }
         if (it <= 1) {  // push_end <= 1: nothing was read back yet
             SB_TRY(read_ctl());
@@ -199,7 +234,7 @@ int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev
     // ---- "spin" phase: terms == max_terms, series not converged. compute_next_term is
     // a no-op (:253-255), the solution no longer changes, the loop keeps re-evaluating the residual every 5th
     // iteration until it is <= tolerance or max_iterations is hit. One evaluation tells all of them. ----
-    if (loop_runs && (max_terms == 0 || (alive && iterations >= max_terms)) && iterations < max_it) {
+    if (!stopped_by_callback && loop_runs && (max_terms == 0 || (alive && iterations >= max_terms)) && iterations < max_it) {
         uint64_t cur = iterations;
         if (identity) {
             // identity mode evaluates nothing further: the residual estimate is frozen
@@ -282,7 +317,7 @@ static int32_t new_solver(uint64_t max_terms, double tol, int adaptive, int cach
 }
 
 // shared front half of the solve entry points: argument checks in the reference's order (NeumannState::new :147-206)
-static int32_t precheck(const sb200_solver *s, const sb200_matrix *m, uint64_t blen, const sb200_options *opt) {
+int32_t sb200::solve_precheck(const sb200_solver *s, const sb200_matrix *m, uint64_t blen, const sb200_options *opt) {
     if (!s || !m) return fail(SB200_ERR_INVALID_INPUT, "null solver or matrix");
     SB_TRY(validate_options(opt));
     if (m->distributed) return fail(SB200_ERR_INVALID_INPUT, "row-block matrix: use sb200_dist_solve");
@@ -351,14 +386,15 @@ static int32_t classify(const sb200_options *opt, const SolveStats &st) {
 }
 
 static int32_t solve_host(const sb200_solver *s, const sb200_matrix *m, const double *b, uint64_t blen,
-                          const sb200_options *opt, double *x_out, bool own_solution, sb200_result *out) {
+                          const sb200_options *opt, double *x_out, bool own_solution, sb200_result *out,
+                          StreamHook *hook = nullptr) {
     clear_error();
     if (!out) return fail(SB200_ERR_INVALID_INPUT, "result is null");
     memset(out, 0, sizeof(*out));
     const double t0 = wall_ms();
     if (!m) return fail(SB200_ERR_INVALID_INPUT, "null matrix");
     DeviceGuard g(m->device);
-    SB_TRY(precheck(s, m, blen, opt));
+    SB_TRY(solve_precheck(s, m, blen, opt));
     if (blen && !b) return fail(SB200_ERR_INVALID_INPUT, "b is null");
     sb200_matrix *mm = const_cast<sb200_matrix *>(m);
     const uint64_t n = m->nrows;
@@ -379,7 +415,17 @@ static int32_t solve_host(const sb200_solver *s, const sb200_matrix *m, const do
         h2d += n * 8;
     }
     SolveStats stats{};
-    SB_TRY(solve_device(s, mm, ws->b.p, x0.p, opt, ws->x.p, st, *ws, stats));
+    struct HookBuf {
+        double *p = nullptr;
+        ~HookBuf() { if (p) pinned_pool_put(p); }
+    } hook_buf;
+    if (hook) {
+        hook_buf.p = (double *)pinned_pool_get(n * 8);
+        if (!hook_buf.p) return fail(SB200_ERR_MEMORY_ALLOCATION, "pinned allocation of %llu bytes failed", (unsigned long long)(n * 8));
+        hook->host_x = hook_buf.p;
+        hook->t0_ms = t0;
+    }
+    SB_TRY(solve_device(s, mm, ws->b.p, x0.p, opt, ws->x.p, st, *ws, stats, hook));
     double *dst = x_out;
     if (own_solution) {
         dst = (double *)pinned_pool_get(n * 8);
@@ -481,7 +527,7 @@ int32_t sb200_solve_dev(const sb200_solver *s, const sb200_matrix *m, const doub
     const double t0 = wall_ms();
     if (!m) return fail(SB200_ERR_INVALID_INPUT, "null matrix");
     DeviceGuard g(m->device);
-    SB_TRY(precheck(s, m, blen, opt));
+    SB_TRY(solve_precheck(s, m, blen, opt));
     if (blen && (!b_dev || !x_dev)) return fail(SB200_ERR_INVALID_INPUT, "null device vector");
     sb200_matrix *mm = const_cast<sb200_matrix *>(m);
     auto ws = matrix_acquire_ws(mm);
@@ -494,6 +540,16 @@ int32_t sb200_solve_dev(const sb200_solver *s, const sb200_matrix *m, const doub
     SB_TRY(solve_device(s, mm, b_dev, opt->initial_guess, opt, x_dev, (cudaStream_t)stream, *ws, stats));
     fill_result(s, opt, stats, *ws, wall_ms() - t0, out);
     return classify(opt, stats);
+}
+
+int32_t sb200_solve_streaming(const sb200_solver *s, const sb200_matrix *m, const double *b, uint64_t blen,
+                              const sb200_options *opt, sb200_stream_callback callback, void *user, sb200_result *out) {
+    if (!opt || !callback || opt->streaming_interval == 0) return solve_host(s, m, b, blen, opt, nullptr, true, out);
+    StreamHook hook;
+    hook.interval = opt->streaming_interval;
+    hook.fn = callback;
+    hook.user = user;
+    return solve_host(s, m, b, blen, opt, nullptr, true, out, &hook);
 }
 
 void sb200_result_free(sb200_result *r) {

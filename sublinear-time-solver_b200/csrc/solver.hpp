@@ -22,7 +22,19 @@ struct SolveStats {
 };
 
 int32_t validate_options(const sb200_options *opt);
+// argument checks of NeumannState::new in the reference's order (neumann.rs:147-206) + cached matrix analysis
+int32_t solve_precheck(const sb200_solver *s, const sb200_matrix *m, uint64_t blen, const sb200_options *opt);
+// streaming (sb200_solve_streaming): every `interval` iterations the loop state is read back anyway; the hook then
+// copies the iterate into `host_x` (pinned, n doubles) and calls `fn`. A non-zero return stops the loop.
+struct StreamHook {
+    uint64_t interval = 0;
+    sb200_stream_callback fn = nullptr;
+    void *user = nullptr;
+    double *host_x = nullptr;
+    double t0_ms = 0.0;
+};
 int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev, const double *x0_dev,
-                     const sb200_options *opt, double *x_out_dev, cudaStream_t st, Workspace &ws, SolveStats &stats);
+                     const sb200_options *opt, double *x_out_dev, cudaStream_t st, Workspace &ws, SolveStats &stats,
+                     const StreamHook *hook = nullptr);
 
 }  // namespace sb200

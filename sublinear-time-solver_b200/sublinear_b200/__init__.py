@@ -28,6 +28,8 @@ MODE_CORRECT, MODE_REF_COMPAT = 0, 1
 DOMINANCE_ROW, DOMINANCE_ROW_OR_COL = 0, 1
 RESIDUAL_EVERY_5, RESIDUAL_IDENTITY = 0, 1
 DUP_KEEP, DUP_SUM = 0, 1
+LAYOUT_CSR, LAYOUT_SELL32 = 0, 1
+STEP_CONTINUE, STEP_CONVERGED = 0, 1
 UNIQUE_ID_BYTES = 128
 
 
@@ -49,6 +51,36 @@ class _Options(C.Structure):
                 ("compute_error_bounds", C.c_int32), ("error_bounds_tolerance", C.c_double),
                 ("enable_profiling", C.c_int32), ("has_random_seed", C.c_int32), ("random_seed", C.c_uint64),
                 ("mode", C.c_int32), ("dominance", C.c_int32), ("residual_check", C.c_int32), ("reserved", C.c_int32)]
+
+
+class _StateInfo(C.Structure):
+    _fields_ = [("dimension", C.c_uint64), ("residual_norm", C.c_double), ("matvec_count", C.c_uint64),
+                ("terms_computed", C.c_uint64), ("series_converged", C.c_int32), ("last_term_norm", C.c_double),
+                ("has_error_bounds", C.c_int32), ("error_upper_bound", C.c_double), ("memory_bytes", C.c_uint64)]
+
+
+class _Partial(C.Structure):
+    _fields_ = [("iteration", C.c_uint64), ("solution", C.POINTER(C.c_double)), ("solution_len", C.c_uint64),
+                ("residual_norm", C.c_double), ("converged", C.c_int32), ("has_estimated_remaining", C.c_int32),
+                ("estimated_remaining", C.c_uint64), ("timestamp_ms", C.c_double)]
+
+
+_STREAM_CB = C.CFUNCTYPE(C.c_int32, C.POINTER(_Partial), C.c_void_p)
+
+
+class _CgConfig(C.Structure):
+    _fields_ = [("max_iterations", C.c_uint64), ("tolerance", C.c_double), ("enable_profiling", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class _CgResult(C.Structure):
+    _fields_ = [("solution", C.POINTER(C.c_double)), ("solution_len", C.c_uint64), ("residual_norm", C.c_double),
+                ("iterations", C.c_uint64), ("converged", C.c_int32), ("breakdown", C.c_int32),
+                ("computation_time_ms", C.c_double), ("matvec_count", C.c_uint64), ("dot_product_count", C.c_uint64),
+                ("axpy_count", C.c_uint64), ("total_flops", C.c_uint64), ("average_bandwidth_gbs", C.c_double),
+                ("average_gflops", C.c_double), ("device_time_ms", C.c_double), ("kernel_launches", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("spmv_kernel_ms", C.c_double),
+                ("spmv_kernel_count", C.c_uint64)]
 
 
 class _Result(C.Structure):
@@ -107,6 +139,7 @@ def lib():
         "sb200_matrix_get": ([vp, u64, u64, P(f64), P(i32)], i32),
         "sb200_matrix_is_diagonally_dominant": ([vp, i32, P(i32)], i32),
         "sb200_matrix_diagonal_dominance_factor": ([vp, P(f64), P(i32)], i32),
+        "sb200_matrix_storage_info": ([vp, P(i32), P(u64), P(u64)], i32),
         "sb200_matrix_export_csr": ([vp, vp, vp, vp], i32),
         "sb200_matrix_multiply_vector": ([vp, vp, u64, vp, u64], i32),
         "sb200_matrix_multiply_vector_add": ([vp, vp, u64, vp, u64], i32),
@@ -130,6 +163,20 @@ def lib():
         "sb200_solve_dev": ([vp, vp, vp, u64, P(_Options), vp, vp, P(_Result)], i32),
         "sb200_result_free": ([P(_Result)], None),
         "sb200_push_iterations_dev": ([vp, vp, u64, u64, vp, vp, vp, vp, P(C.c_float)], i32),
+        "sb200_neumann_initialize": ([vp, vp, vp, u64, P(_Options), P(vp)], i32),
+        "sb200_state_step": ([vp, P(i32)], i32),
+        "sb200_state_is_converged": ([vp, P(i32)], i32),
+        "sb200_state_extract_solution": ([vp, vp, u64], i32),
+        "sb200_state_update_rhs": ([vp, vp, vp, u64], i32),
+        "sb200_state_reset": ([vp], i32),
+        "sb200_state_info": ([vp, P(_StateInfo)], i32),
+        "sb200_state_free": ([vp], None),
+        "sb200_solve_streaming": ([vp, vp, vp, u64, P(_Options), _STREAM_CB, vp, P(_Result)], i32),
+        "sb200_cg_config_default": ([P(_CgConfig)], None),
+        "sb200_cg_solve": ([vp, vp, u64, P(_CgConfig), P(_CgResult)], i32),
+        "sb200_cg_solve_into": ([vp, vp, u64, P(_CgConfig), vp, P(_CgResult)], i32),
+        "sb200_cg_solve_dev": ([vp, vp, u64, P(_CgConfig), vp, vp, P(_CgResult)], i32),
+        "sb200_cg_result_free": ([P(_CgResult)], None),
         "sb200_solve_entry": ([vp, vp, u64, vp, u64, f64, u64, u64, u64, vp, vp], i32),
         "sb200_pagerank_system": ([vp, vp, vp, u64, u64, f64, P(vp), vp], i32),
         "sb200_gen_bench_csr": ([u64, f64, u64, u64, vp, vp, vp, vp, P(u64)], i32),
@@ -400,6 +447,12 @@ class SparseMatrix:
     def scale(self, factor):
         _check(lib().sb200_matrix_scale(self._h, factor))
 
+    def storage_info(self):
+        """Device layout the hot kernels read: {'layout': LAYOUT_CSR | LAYOUT_SELL32, 'slots', 'device_bytes'}."""
+        lay, slots, nbytes = C.c_int32(), C.c_uint64(), C.c_uint64()
+        _check(lib().sb200_matrix_storage_info(self._h, C.byref(lay), C.byref(slots), C.byref(nbytes)))
+        return {"layout": lay.value, "slots": slots.value, "device_bytes": nbytes.value}
+
     def to_csr(self):
         n, nnz = self.rows(), self.nnz()
         rp, ci, v = np.zeros(n + 1, np.uint64), np.zeros(nnz, np.uint32), np.zeros(nnz)
@@ -486,6 +539,42 @@ class NeumannSolver:
         _check(rc, res)
         return res
 
+    def initialize(self, matrix: SparseMatrix, b, options: SolverOptions | None = None) -> "NeumannState":
+        """`SolverAlgorithm::initialize` (src/solver/neumann.rs:381-388): the stepping interface."""
+        options = options or SolverOptions()
+        b = _f64(b)
+        guess = None if options.initial_guess is None else _f64(options.initial_guess)
+        o = options._c(None if guess is None else guess.ctypes.data, 0 if guess is None else len(guess))
+        h = C.c_void_p()
+        _check(lib().sb200_neumann_initialize(self._h, matrix._h, _ptr(b), len(b), C.byref(o), C.byref(h)))
+        return NeumannState(h, matrix)
+
+    def solve_streaming(self, matrix: SparseMatrix, b, options: SolverOptions, callback) -> SolverResult:
+        """`solve` with `SolverOptions::streaming(interval)`: `callback(partial: dict) -> bool | None` receives a
+        PartialSolution (src/solver/mod.rs:198-217) every `streaming_interval` iterations; return True to stop."""
+        b = _f64(b)
+        o = options._c()
+
+        def _cb(pp, _user):
+            p = pp.contents
+            sol = np.ctypeslib.as_array(p.solution, shape=(max(int(p.solution_len), 1),))[:int(p.solution_len)].copy()
+            stop = callback({"iteration": int(p.iteration), "solution": sol, "residual_norm": p.residual_norm,
+                             "converged": bool(p.converged),
+                             "estimated_remaining": int(p.estimated_remaining) if p.has_estimated_remaining else None,
+                             "timestamp_ms": p.timestamp_ms})
+            return 1 if stop else 0
+
+        cb = _STREAM_CB(_cb)
+        r = _Result()
+        rc = lib().sb200_solve_streaming(self._h, matrix._h, _ptr(b), len(b), C.byref(o), cb, None, C.byref(r))
+        sol = None
+        if r.solution:
+            sol = np.ctypeslib.as_array(r.solution, shape=(max(int(r.solution_len), 1),))[:int(r.solution_len)].copy()
+        res = SolverResult._from(r, sol)
+        lib().sb200_result_free(C.byref(r))
+        _check(rc, res)
+        return res
+
     def solve_dev(self, matrix: SparseMatrix, b_ptr: int, n: int, x_ptr: int, options: SolverOptions | None = None,
                   stream: int = 0, guess_ptr: int | None = None) -> SolverResult:
         """Inputs/outputs already resident in HBM (raw device pointers, e.g. torch tensor.data_ptr())."""
@@ -496,6 +585,150 @@ class NeumannSolver:
         res = SolverResult._from(r, None)
         _check(rc, res)
         return res
+
+
+@dataclass
+class OptimizedSolverConfig:
+    """`OptimizedSolverConfig` (src/optimized_solver.rs:108-127)."""
+    max_iterations: int = 1000
+    tolerance: float = 1e-6
+    enable_profiling: bool = False
+
+    def _c(self):
+        c = _CgConfig()
+        lib().sb200_cg_config_default(C.byref(c))
+        c.max_iterations, c.tolerance, c.enable_profiling = self.max_iterations, self.tolerance, int(self.enable_profiling)
+        return c
+
+
+@dataclass
+class OptimizedSolverResult:
+    """`OptimizedSolverResult` + `OptimizedSolverStats` (src/optimized_solver.rs:130-166) + extension fields."""
+    solution: np.ndarray | None
+    residual_norm: float
+    iterations: int
+    converged: bool
+    breakdown: bool
+    computation_time_ms: float
+    matvec_count: int
+    dot_product_count: int
+    axpy_count: int
+    total_flops: int
+    average_bandwidth_gbs: float
+    average_gflops: float
+    device_time_ms: float
+    kernel_launches: int
+    h2d_bytes: int
+    d2h_bytes: int
+    spmv_kernel_ms: float
+    spmv_kernel_count: int
+
+    @staticmethod
+    def _from(r: _CgResult, solution):
+        return OptimizedSolverResult(solution, r.residual_norm, int(r.iterations), bool(r.converged), bool(r.breakdown),
+                                     r.computation_time_ms, int(r.matvec_count), int(r.dot_product_count),
+                                     int(r.axpy_count), int(r.total_flops), r.average_bandwidth_gbs, r.average_gflops,
+                                     r.device_time_ms, int(r.kernel_launches), int(r.h2d_bytes), int(r.d2h_bytes),
+                                     r.spmv_kernel_ms, int(r.spmv_kernel_count))
+
+    def data(self):
+        return self.solution
+
+
+class OptimizedConjugateGradientSolver:
+    """`OptimizedConjugateGradientSolver` (src/optimized_solver.rs:168-295); the loop shared with FastConjugateGradient
+    (src/fast_solver.rs:111-178) and UltraFastCG (src/ultra_fast.rs:100-158), on the push path's SpMV kernel."""
+
+    def __init__(self, config: OptimizedSolverConfig | None = None):
+        self.config = config or OptimizedSolverConfig()
+        self._last = None
+
+    @staticmethod
+    def new(config: OptimizedSolverConfig):
+        return OptimizedConjugateGradientSolver(config)
+
+    def solve(self, matrix: SparseMatrix, b, out=None) -> OptimizedSolverResult:
+        b = _f64(b)
+        c = self.config._c()
+        r = _CgResult()
+        if out is not None:
+            rc = lib().sb200_cg_solve_into(matrix._h, _ptr(b), len(b), C.byref(c), _ptr(out), C.byref(r))
+            res = OptimizedSolverResult._from(r, out)
+        else:
+            rc = lib().sb200_cg_solve(matrix._h, _ptr(b), len(b), C.byref(c), C.byref(r))
+            sol = None
+            if r.solution:
+                sol = np.ctypeslib.as_array(r.solution, shape=(max(int(r.solution_len), 1),))[:int(r.solution_len)].copy()
+            res = OptimizedSolverResult._from(r, sol)
+            lib().sb200_cg_result_free(C.byref(r))
+        _check(rc, res)
+        self._last = res
+        return res
+
+    def solve_dev(self, matrix: SparseMatrix, b_ptr: int, n: int, x_ptr: int, stream: int = 0) -> OptimizedSolverResult:
+        c = self.config._c()
+        r = _CgResult()
+        rc = lib().sb200_cg_solve_dev(matrix._h, b_ptr, n, C.byref(c), x_ptr, stream or None, C.byref(r))
+        res = OptimizedSolverResult._from(r, None)
+        _check(rc, res)
+        self._last = res
+        return res
+
+    def get_last_iteration_count(self):
+        """`get_last_iteration_count` returns stats.matvec_count in the reference (src/optimized_solver.rs:323-325)."""
+        return self._last.matvec_count if self._last else 0
+
+
+class NeumannState:
+    """`NeumannState` behind `SolverAlgorithm::{step, is_converged, extract_solution, update_rhs}` and
+    `SolverState::{residual_norm, matvec_count, error_bounds, reset}` (src/solver/neumann.rs:97-135, 350-462)."""
+
+    def __init__(self, handle, matrix):
+        self._h = handle
+        self._matrix = matrix   # the state points into the matrix handle: keep it alive
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.sb200_state_free(self._h)
+            self._h = None
+
+    def step(self) -> int:
+        out = C.c_int32()
+        _check(lib().sb200_state_step(self._h, C.byref(out)))
+        return out.value
+
+    def is_converged(self) -> bool:
+        out = C.c_int32()
+        _check(lib().sb200_state_is_converged(self._h, C.byref(out)))
+        return bool(out.value)
+
+    def info(self) -> dict:
+        i = _StateInfo()
+        _check(lib().sb200_state_info(self._h, C.byref(i)))
+        return {"dimension": i.dimension, "residual_norm": i.residual_norm, "matvec_count": i.matvec_count,
+                "terms_computed": i.terms_computed, "series_converged": bool(i.series_converged),
+                "last_term_norm": i.last_term_norm,
+                "error_upper_bound": i.error_upper_bound if i.has_error_bounds else None, "memory_bytes": i.memory_bytes}
+
+    def residual_norm(self) -> float:
+        return self.info()["residual_norm"]
+
+    def matvec_count(self) -> int:
+        return self.info()["matvec_count"]
+
+    def extract_solution(self) -> np.ndarray:
+        x = np.zeros(self.info()["dimension"])
+        _check(lib().sb200_state_extract_solution(self._h, _ptr(x), len(x)))
+        return x
+
+    def update_rhs(self, delta_b):
+        """`update_rhs(&mut state, &[(index, delta)])`"""
+        idx = _u64([i for i, _ in delta_b])
+        dl = _f64([d for _, d in delta_b])
+        _check(lib().sb200_state_update_rhs(self._h, _ptr(idx), _ptr(dl), len(dl)))
+
+    def reset(self):
+        _check(lib().sb200_state_reset(self._h))
 
 
 def push_iterations_dev(matrix: SparseMatrix, b_ptr: int, n: int, nterms: int, x_ptr: int = 0, t_ptr: int = 0,

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <utility>
 
 #include "../../sublinear-time-solver_b200/cpp/sublinear.hpp"
 
@@ -74,6 +75,32 @@ int main() {
         try { SparseMatrix::from_triplets({{2, 0, 1.0}}, 2, 2); } catch (const SolverError &e) { oob = e.kind == ErrorKind::IndexOutOfBounds; }
         try { SparseMatrix::from_triplets({{0, 0, NAN}}, 2, 2); } catch (const SolverError &e) { nonfinite = e.kind == ErrorKind::InvalidInput; }
         CHECK(oob && nonfinite);
+    }
+    {  // optimized_solver.rs:380-396 test_optimized_matrix_creation / test_optimized_matrix_vector_multiply
+        auto m = OptimizedSparseMatrix::from_triplets({{0, 0, 4.0}, {0, 1, 1.0}, {1, 0, 1.0}, {1, 1, 3.0}}, 2, 2);
+        CHECK(m.dimensions() == std::make_pair(size_t(2), size_t(2)) && m.nnz() == 4);
+        std::vector<double> x{1.0, 2.0}, y(2, 0.0);
+        m.multiply_vector(x, y);
+        CHECK(y[0] == 6.0 && y[1] == 7.0);
+        CHECK(m.get_performance_stats().first == 1 && m.get_performance_stats().second == 4 * 8 + 2 * 8 + 2 * 8);
+        m.reset_stats();
+        CHECK(m.get_performance_stats().first == 0);
+    }
+    {  // optimized_solver.rs:398-435 test_optimized_conjugate_gradient / test_solver_performance_stats
+        auto m = OptimizedSparseMatrix::from_triplets({{0, 0, 4.0}, {0, 1, 1.0}, {1, 0, 1.0}, {1, 1, 3.0}}, 2, 2);
+        std::vector<double> b{1.0, 2.0};
+        OptimizedConjugateGradientSolver solver(OptimizedSolverConfig{});
+        auto r = solver.solve(m, b);
+        CHECK(r.converged && r.residual_norm < 1e-6 && r.iterations > 0);
+        std::vector<double> ax(2, 0.0);
+        m.multiply_vector(r.solution, ax);
+        CHECK(std::sqrt((ax[0] - b[0]) * (ax[0] - b[0]) + (ax[1] - b[1]) * (ax[1] - b[1])) < 1e-10);
+        CHECK(r.performance_stats.matvec_count > 0 && r.performance_stats.dot_product_count > 0 &&
+              r.performance_stats.total_flops > 0);
+        CHECK(solver.get_last_iteration_count() == r.performance_stats.matvec_count && r.data().size() == 2);
+        bool threw = false;  // "Right-hand side vector length must match matrix size" (:191-193)
+        try { solver.solve(m, {1.0, 2.0, 3.0}); } catch (const SolverError &e) { threw = e.kind == ErrorKind::DimensionMismatch; }
+        CHECK(threw);
     }
     std::printf("reference unit tests: all passed\n");
     return 0;

@@ -25,4 +25,4 @@ for _ in range(3):
     best = min(best, ms / 12 * 1e3)
 alg = 12 * len(v) + 44 * n + 4
 env = {k: v_ for k, v_ in os.environ.items() if k.startswith("SUBLINEAR_B200")}
-print(f"{wl} n={n} nnz={len(v)} {env}: push {best:.1f} us  {alg / best / 1e3:.0f} GB/s  frac {alg / best / 1e3 / 6554.6:.3f}", flush=True)
+print(f"{wl} n={n} nnz={len(v)} layout={m.storage_info()['layout']} {env}: push {best:.1f} us  {alg / best / 1e3:.0f} GB/s  frac {alg / best / 1e3 / 6554.6:.3f}", flush=True)
