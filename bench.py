@@ -12,8 +12,9 @@ MODE_CORRECT, the reference's residual-every-5th-iteration cadence).
           around every push launch inside the timed steps) vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline : the oracle's restatement of the reference's rayon row-chunk SpMV (src/simd_ops.rs:202-239) inside
           the same recurrence, all host cores, bounded sample
-N > 1 (torchrun, one rank per GPU): STRONG scaling on the same 10 M system — contiguous row blocks, one NCCL
-allgather of the term slice + a 2-double allreduce per term (sb200_dist_solve).
+N > 1 (torchrun, one rank per GPU): STRONG scaling on the same 10 M system — contiguous row blocks, one exchange of
+the term slice + two partial sums per term (sb200_dist_solve: fused peer-memory stores by default,
+SUBLINEAR_B200_DIST=nccl for the allgather + allreduce flavour).
 `--impl reference`: the reference's CPU path (oracle port; no Rust toolchain in this image) on the host cores.
 """
 import argparse
@@ -394,7 +395,9 @@ def main():
                        "mode": args.mode, "terms_per_step": r_last.terms_computed, "matvecs_per_step": r_last.matvec_count,
                        "iterations_per_step": r_last.iterations, "converged": r_last.converged,
                        "l2_policy": "inputs larger than L2 (1.2 GB CSR stream per SpMV vs 126 MB L2), no flush",
-                       "parallelism": "single GPU" if not dist else f"row blocks x{world}, NCCL allgather of the term slice per term",
+                       "parallelism": "single GPU" if not dist else (f"row blocks x{world}, term slice exchanged per term: " +
+                                                      ("NCCL allgather + allreduce" if os.environ.get("SUBLINEAR_B200_DIST") == "nccl"
+                                                       else "fused peer-memory stores from the push kernel (CUDA IPC over NVLink)")),
                        "rel_residual": rel_res, "setup_s": t_gen,
                        "device_layout": "SELL-32" if layout["layout"] == sb.LAYOUT_SELL32 else "CSR",
                        "value_slots_streamed_per_spmv": layout["slots"], "matrix_device_bytes": layout["device_bytes"]},

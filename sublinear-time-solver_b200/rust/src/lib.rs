@@ -6,11 +6,31 @@
 use std::os::raw::c_char;
 
 use sublinear::error::{Result, SolverError};
-use sublinear::solver::{SolverOptions, SolverResult};
-use sublinear::types::{Precision, SolverStats};
+use sublinear::solver::{SolverOptions, SolverResult, SolverState, StepResult};
+use sublinear::types::{ErrorBoundMethod, ErrorBounds, MemoryInfo, Precision, SolverStats};
 
 #[repr(C)] pub struct sb200_matrix { _p: [u8; 0] }
 #[repr(C)] pub struct sb200_solver { _p: [u8; 0] }
+#[repr(C)] pub struct sb200_state { _p: [u8; 0] }
+
+#[repr(C)]
+pub struct sb200_state_info_t {
+    pub dimension: u64, pub residual_norm: f64, pub matvec_count: u64, pub terms_computed: u64,
+    pub series_converged: i32, pub last_term_norm: f64, pub has_error_bounds: i32, pub error_upper_bound: f64,
+    pub memory_bytes: u64,
+}
+
+#[repr(C)]
+pub struct sb200_cg_config { pub max_iterations: u64, pub tolerance: f64, pub enable_profiling: i32, pub reserved: i32 }
+
+#[repr(C)]
+pub struct sb200_cg_result {
+    pub solution: *mut f64, pub solution_len: u64, pub residual_norm: f64, pub iterations: u64, pub converged: i32,
+    pub breakdown: i32, pub computation_time_ms: f64, pub matvec_count: u64, pub dot_product_count: u64,
+    pub axpy_count: u64, pub total_flops: u64, pub average_bandwidth_gbs: f64, pub average_gflops: f64,
+    pub device_time_ms: f64, pub kernel_launches: u64, pub h2d_bytes: u64, pub d2h_bytes: u64,
+    pub spmv_kernel_ms: f64, pub spmv_kernel_count: u64,
+}
 
 #[repr(C)]
 pub struct sb200_options {
@@ -41,6 +61,20 @@ extern "C" {
     fn sb200_options_default(o: *mut sb200_options);
     fn sb200_solve_into(s: *const sb200_solver, m: *const sb200_matrix, b: *const f64, blen: u64,
                         opt: *const sb200_options, x_out: *mut f64, out: *mut sb200_result) -> i32;
+    // trait SolverAlgorithm / SolverState (src/solver/mod.rs:223-352)
+    fn sb200_neumann_initialize(s: *const sb200_solver, m: *const sb200_matrix, b: *const f64, blen: u64,
+                                opt: *const sb200_options, out: *mut *mut sb200_state) -> i32;
+    fn sb200_state_step(st: *mut sb200_state, step_result: *mut i32) -> i32;
+    fn sb200_state_is_converged(st: *const sb200_state, out: *mut i32) -> i32;
+    fn sb200_state_extract_solution(st: *const sb200_state, x: *mut f64, xlen: u64) -> i32;
+    fn sb200_state_update_rhs(st: *mut sb200_state, indices: *const u64, deltas: *const f64, count: u64) -> i32;
+    fn sb200_state_reset(st: *mut sb200_state) -> i32;
+    fn sb200_state_info(st: *const sb200_state, info: *mut sb200_state_info_t) -> i32;
+    fn sb200_state_free(st: *mut sb200_state);
+    // OptimizedConjugateGradientSolver (src/optimized_solver.rs:168-295)
+    fn sb200_cg_config_default(c: *mut sb200_cg_config);
+    fn sb200_cg_solve_into(m: *const sb200_matrix, b: *const f64, blen: u64, cfg: *const sb200_cg_config,
+                           x_out: *mut f64, out: *mut sb200_cg_result) -> i32;
 }
 
 fn last_error() -> String {
@@ -127,3 +161,88 @@ impl B200NeumannSolver {
     }
 }
 impl Drop for B200NeumannSolver { fn drop(&mut self) { unsafe { sb200_solver_free(self.h) } } }
+
+/// `NeumannState` on the device (src/solver/neumann.rs:97-135). The C state shares ownership of the matrix handle, so
+/// it may outlive the `B200Matrix` it was initialised from.
+pub struct B200NeumannState { h: *mut sb200_state }
+unsafe impl Send for B200NeumannState {}
+
+impl B200NeumannState {
+    fn info(&self) -> sb200_state_info_t {
+        let mut i: sb200_state_info_t = unsafe { std::mem::zeroed() };
+        unsafe { sb200_state_info(self.h, &mut i) };
+        i
+    }
+}
+impl Drop for B200NeumannState { fn drop(&mut self) { unsafe { sb200_state_free(self.h) } } }
+
+/// trait SolverState (src/solver/mod.rs:336-352; NeumannState impl src/solver/neumann.rs:350-378)
+impl SolverState for B200NeumannState {
+    fn residual_norm(&self) -> Precision { self.info().residual_norm }
+    fn matvec_count(&self) -> usize { self.info().matvec_count as usize }
+    fn error_bounds(&self) -> Option<ErrorBounds> {
+        let i = self.info();
+        if i.has_error_bounds != 0 { Some(ErrorBounds::upper_bound_only(i.error_upper_bound, ErrorBoundMethod::NeumannTruncation)) } else { None }
+    }
+    fn memory_usage(&self) -> MemoryInfo {
+        let b = self.info().memory_bytes as usize;
+        MemoryInfo { current_usage_bytes: b, peak_usage_bytes: b, matrix_memory_bytes: 0, vector_memory_bytes: b,
+                     workspace_memory_bytes: 0, allocation_count: 1, deallocation_count: 0 }
+    }
+    fn reset(&mut self) { unsafe { sb200_state_reset(self.h) }; }
+}
+
+/// The stepping half of trait SolverAlgorithm (src/solver/mod.rs:223-252) for the B200 solver. `initialize` takes the
+/// device-resident matrix; a blanket `impl SolverAlgorithm` would first convert `&dyn Matrix` with `to_triplets()`.
+impl B200NeumannSolver {
+    pub fn initialize(&self, matrix: &B200Matrix, b: &[Precision], options: &SolverOptions) -> Result<B200NeumannState> {
+        let mut o: sb200_options = unsafe { std::mem::zeroed() };
+        unsafe { sb200_options_default(&mut o) };
+        o.tolerance = options.tolerance;
+        o.max_iterations = options.max_iterations as u64;
+        if let Some(ref g) = options.initial_guess { o.initial_guess = g.as_ptr(); o.initial_guess_len = g.len() as u64; }
+        let mut h = std::ptr::null_mut();
+        let rc = unsafe { sb200_neumann_initialize(self.h, matrix.h, b.as_ptr(), b.len() as u64, &o, &mut h) };
+        if rc != 0 { return Err(to_error(rc, &unsafe { std::mem::zeroed() }, options.tolerance)); }
+        Ok(B200NeumannState { h })
+    }
+    /// The body the reference left commented out (src/solver/neumann.rs:404-418).
+    pub fn step(&self, state: &mut B200NeumannState) -> Result<StepResult> {
+        let mut r = 0i32;
+        let rc = unsafe { sb200_state_step(state.h, &mut r) };
+        if rc != 0 { return Err(to_error(rc, &unsafe { std::mem::zeroed() }, 0.0)); }
+        Ok(if r == 1 { StepResult::Converged } else { StepResult::Continue })
+    }
+    pub fn is_converged(&self, state: &B200NeumannState) -> bool {
+        let mut c = 0i32;
+        unsafe { sb200_state_is_converged(state.h, &mut c) };
+        c != 0
+    }
+    pub fn extract_solution(&self, state: &B200NeumannState) -> Vec<Precision> {
+        let mut x = vec![0.0; state.info().dimension as usize];
+        unsafe { sb200_state_extract_solution(state.h, x.as_mut_ptr(), x.len() as u64) };
+        x
+    }
+    pub fn update_rhs(&self, state: &mut B200NeumannState, delta_b: &[(usize, Precision)]) -> Result<()> {
+        let idx: Vec<u64> = delta_b.iter().map(|d| d.0 as u64).collect();
+        let dl: Vec<f64> = delta_b.iter().map(|d| d.1).collect();
+        let rc = unsafe { sb200_state_update_rhs(state.h, idx.as_ptr(), dl.as_ptr(), dl.len() as u64) };
+        if rc != 0 { Err(to_error(rc, &unsafe { std::mem::zeroed() }, 0.0)) } else { Ok(()) }
+    }
+    pub fn algorithm_name(&self) -> &'static str { "neumann" }
+}
+
+/// `OptimizedConjugateGradientSolver::solve` (src/optimized_solver.rs:182-295) on the same SpMV kernel.
+/// Returns (solution, residual_norm, iterations, converged) — the fields of `OptimizedSolverResult`.
+pub fn b200_cg_solve(matrix: &B200Matrix, b: &[Precision], max_iterations: usize, tolerance: Precision)
+                     -> std::result::Result<(Vec<Precision>, Precision, usize, bool), String> {
+    let mut c: sb200_cg_config = unsafe { std::mem::zeroed() };
+    unsafe { sb200_cg_config_default(&mut c) };
+    c.max_iterations = max_iterations as u64;
+    c.tolerance = tolerance;
+    let mut x = vec![0.0; b.len()];
+    let mut r: sb200_cg_result = unsafe { std::mem::zeroed() };
+    let rc = unsafe { sb200_cg_solve_into(matrix.h, b.as_ptr(), b.len() as u64, &c, x.as_mut_ptr(), &mut r) };
+    if rc != 0 { return Err(last_error()); }   // "Matrix must be square" / length mismatch (:188-193)
+    Ok((x, r.residual_norm, r.iterations as usize, r.converged != 0))
+}
