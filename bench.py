@@ -328,8 +328,10 @@ def main():
     peak, peak_src = measured_peak()
     roofline = None
     layout = m.storage_info()
-    kernel_name = ("sell_kernel<EPI_PUSH,256,8> (SELL-32 layout, no shared memory)" if layout["layout"] == sb.LAYOUT_SELL32
-                   else "warp_kernel<EPI_PUSH,256,4> (CSR slices)")
+    kernel_name = {sb.LAYOUT_SELL32: "sell_kernel<EPI_PUSH,256,8> (SELL-32 layout, no shared memory)",
+                   sb.LAYOUT_CSR_SLABS: "warp_kernel<EPI_PUSH,256,4>, one pass per column slab of the term vector "
+                                        "(the measured launch is the whole pass set)",
+                   sb.LAYOUT_CSR: "warp_kernel<EPI_PUSH,256,4> (CSR slices)"}[layout["layout"]]
     if push_cnt:
         t_push = push_ms / push_cnt * 1e-3
         alg = algorithmic_bytes_push(n_local, nnz_local) + (8 * (size - n_local) if dist else 0)
@@ -399,7 +401,7 @@ def main():
                                                       ("NCCL allgather + allreduce" if os.environ.get("SUBLINEAR_B200_DIST") == "nccl"
                                                        else "fused peer-memory stores from the push kernel (CUDA IPC over NVLink)")),
                        "rel_residual": rel_res, "setup_s": t_gen,
-                       "device_layout": "SELL-32" if layout["layout"] == sb.LAYOUT_SELL32 else "CSR",
+                       "device_layout": {sb.LAYOUT_SELL32: "SELL-32", sb.LAYOUT_CSR_SLABS: "CSR column slabs", sb.LAYOUT_CSR: "CSR"}[layout["layout"]],
                        "value_slots_streamed_per_spmv": layout["slots"], "matrix_device_bytes": layout["device_bytes"]},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_local * world if dist else 8 * n_local,

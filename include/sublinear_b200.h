@@ -173,9 +173,11 @@ int32_t sb200_matrix_is_diagonally_dominant(const sb200_matrix *m, int32_t domin
 int32_t sb200_matrix_diagonal_dominance_factor(const sb200_matrix *m, double *factor, int32_t *present);
 /* Device layout the hot kernels read (extension; the CSRStorage slices stay the ingest / export format):
  * layout 0 = the CSR slices as uploaded, 1 = an additional SELL-32 copy (blocks of 32 rows, element k of row r at
- * slab*32 + k*32 + r, zero-padded to the longest row of the block) chosen when it costs <= 25 % extra slots.
- * slots = value slots the kernels stream per SpMV (= nnz for layout 0); device_bytes = all matrix arrays. */
-enum { SB200_LAYOUT_CSR = 0, SB200_LAYOUT_SELL32 = 1 };
+ * slab*32 + k*32 + r, zero-padded to the longest row of the block) chosen when it costs <= 25 % extra slots,
+ * 2 = an additional copy regrouped into 2..4 column slabs (one kernel pass per slab; chosen when the gathered vector
+ * does not fit the L2 partition of a die, i.e. 8*ncols > 48 MB). Results are bit-identical in all three.
+ * slots = value slots the kernels stream per SpMV (= nnz for layouts 0 and 2); device_bytes = all matrix arrays. */
+enum { SB200_LAYOUT_CSR = 0, SB200_LAYOUT_SELL32 = 1, SB200_LAYOUT_CSR_SLABS = 2 };
 int32_t sb200_matrix_storage_info(const sb200_matrix *m, int32_t *layout, uint64_t *slots, uint64_t *device_bytes);
 /* CSRStorage::to_triplets / SparseMatrix::as_csr (src/matrix/sparse.rs:210-227, mod.rs:313-319): copy out.
  * Any output pointer may be NULL. row_ptr has nrows+1 entries. */

@@ -86,6 +86,7 @@ int32_t cg_device(sb200_matrix *m, const double *b_dev, const sb200_cg_config *c
     spmv.out = ap;
     spmv.ctl = ws.ctl.p;
     spmv.partials = ws.partials.p;
+    spmv.acc = ws.tmp.p;
 
     CgVecArgs va{};
     va.b = b_dev;
@@ -129,7 +130,7 @@ int32_t cg_device(sb200_matrix *m, const double *b_dev, const sb200_cg_config *c
             SB_TRY(launch_cg_vec(va, st));
             va.phase = 2;
             SB_TRY(launch_cg_vec(va, st));
-            launches += 3;
+            launches += 2 + (m->nslabs > 1 ? (uint64_t)m->nslabs : 1);
         }
         SB_TRY(read_ctl());
         alive = ws.h_ctl->alive != 0;

@@ -133,6 +133,8 @@ struct PeerExchange {               // all zero = not used (single GPU, or the N
     unsigned long long *flags[kMaxPeers];  // peer p's flag array [world]
 };
 
+constexpr int kMaxSlabs = 4;  // column slabs of the gather source (matrix.cu build_slabs)
+
 enum Epilogue { EPI_SPMV = 0, EPI_PUSH = 1, EPI_RESID = 2, EPI_CG = 3 };  // EPI_CG: out = A p and sum p_i (A p)_i (warp-stream kernel only)
 
 struct TileKernelArgs {
@@ -147,6 +149,15 @@ struct TileKernelArgs {
     const uint32_t *sell_ptr;   // nblocks + 1 slab offsets (slab = 32 slots, one per row of the block)
     const uint32_t *sell_cols;
     const double *sell_vals;
+    // the same matrix split into column slabs (matrix.cu build_slabs): nslabs > 1 -> launch_tile_kernel runs one pass of
+    // the warp-stream kernel per slab over slab-local CSR slices; row sums carry over from pass to pass through `acc`
+    int nslabs;
+    const double *slab_vals[kMaxSlabs];
+    const uint32_t *slab_cols[kMaxSlabs];
+    const uint32_t *slab_row_ptr[kMaxSlabs];
+    double *acc;           // n doubles of scratch for the partial row sums; null: `out` carries them
+    const double *acc_in;  // set per pass by the launcher: continue these sums (null in the first pass)
+    double *acc_out;       // set per pass by the launcher: store the sums instead of running the epilogue (null in the last)
     // vectors
     const double *xin;    // gather source (term / solution / x)
     const double *xin_own; // value of xin for local row i is xin_own[i] (== xin + row_base)
@@ -183,6 +194,14 @@ struct SetupOut {
 };
 int32_t launch_setup_rows(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
                           uint32_t row_base, int compat_diag, SetupOut out, cudaStream_t stream);
+// column-slab split at ingest: counts per (row, slab), then the ordered fill; `unsorted` receives 1 if some row is not
+// sorted by column (then the split would change the accumulation order and is not used)
+int32_t launch_slab_count(const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows, uint32_t slab_width, int nslabs,
+                          uint32_t *const *counts, int *unsorted, cudaStream_t stream);
+int32_t launch_slab_fill(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
+                         uint32_t slab_width, int nslabs, const uint32_t *const *slab_row_ptr, uint32_t *const *slab_cols,
+                         double *const *slab_vals, cudaStream_t stream);
+int32_t device_exclusive_scan_u32(uint32_t *data, uint64_t n, uint64_t *total, cudaStream_t stream);
 int32_t launch_csr_to_sell(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
                            const uint32_t *sell_ptr, uint32_t *sell_cols, double *sell_vals, cudaStream_t stream);
 int32_t launch_col_dominance(const double *col_diag, const double *col_off, uint32_t n, unsigned long long *first_bad,

@@ -334,7 +334,7 @@ int32_t sb200_dist_matrix_from_csr(sb200_comm *c, uint64_t n_global, uint64_t ro
                     (unsigned long long)e0, (unsigned long long)e1, (unsigned long long)row0, (unsigned long long)row1);
     SB_TRY(sb200_set_device(c->device));
     const uint64_t nloc = row1 - row0;
-    SB_TRY(matrix_from_host_csr(row_ptr, nullptr, col_indices, values, nloc, n_global, row_ptr[nloc], true, out));
+    SB_TRY(matrix_from_host_csr(row_ptr, nullptr, col_indices, values, nloc, n_global, row_ptr[nloc], true, out, false));
     (*out)->distributed = true;
     (*out)->tile_cfg = -1;  // the fused exchange lives in the warp-stream kernel
     (*out)->row_base = row0;

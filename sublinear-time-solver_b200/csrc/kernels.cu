@@ -648,6 +648,23 @@ static int32_t launch_warp_any(Epilogue epi, const TileKernelArgs &a, cudaStream
 static int32_t launch_sell_any(Epilogue epi, const TileKernelArgs &a, cudaStream_t stream, int *mg);
 
 int32_t launch_tile_kernel(int cfg, Epilogue epi, const TileKernelArgs &a, cudaStream_t stream) {
+    if (cfg < 0 && a.nslabs > 1) {
+        // column-slab passes: the gather source of one pass is a slab of the vector small enough to stay in the L2
+        // partition of each die; the row sums continue from pass to pass in column = CSR order
+        double *acc = a.acc ? a.acc : a.out;
+        if (!acc) return fail(SB200_ERR_ALGORITHM, "column-slab passes need a buffer for the partial row sums");
+        for (int s = 0; s < a.nslabs; s++) {
+            TileKernelArgs p = a;
+            p.vals = a.slab_vals[s];
+            p.cols = a.slab_cols[s];
+            p.row_ptr = a.slab_row_ptr[s];
+            p.sell_ptr = nullptr;
+            p.acc_in = s > 0 ? acc : nullptr;
+            p.acc_out = s + 1 < a.nslabs ? acc : nullptr;
+            SB_TRY(launch_warp_any(epi, p, stream, nullptr));
+        }
+        return SB200_OK;
+    }
     if (cfg < 0 && a.sell_ptr != nullptr) return launch_sell_any(epi, a, stream, nullptr);
     if (cfg < 0) return launch_warp_any(epi, a, stream, nullptr);
     if (epi == EPI_CG) return fail(SB200_ERR_INVALID_INPUT, "the CG epilogue exists in the warp-stream kernel only");
@@ -764,8 +781,11 @@ __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
         const uint32_t b0 = __shfl_sync(0xffffffffu, rs, 0);
         const uint32_t b1 = __shfl_sync(0xffffffffu, re, (int)(rlast & 31u));
         double own = 0.0, dv = 0.0, xs = 0.0, rh = 0.0;
-        if (active) row_operands<EPI>(a, row, own, dv, xs, rh);
+        // column-slab passes (launch_tile_kernel): only the last pass runs the epilogue, the others hand the running
+        // row sums on through acc_out -> acc_in; the order of the additions is the single-pass order
+        if (active && (a.acc_out == nullptr || (EPI == EPI_SPMV && a.acc_in == nullptr))) row_operands<EPI>(a, row, own, dv, xs, rh);
         double acc = (EPI == EPI_SPMV && a.accumulate) ? xs : 0.0;
+        if (a.acc_in != nullptr) acc = active ? a.acc_in[row] : 0.0;
         const uint32_t max_len = __reduce_max_sync(0xffffffffu, re - rs);
         if (max_len <= kLongRow) {
             for (uint32_t c0 = b0 & ~(uint32_t)(EPL - 1); c0 < b1; c0 += CH) {
@@ -825,9 +845,12 @@ __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
                 if ((uint32_t)lane == i) acc += part;
             }
         }
-        if (active) row_epilogue<EPI>(a, row, acc, own, dv, xs, rh, sq, aux);
+        if (active) {
+            if (a.acc_out != nullptr) a.acc_out[row] = acc;
+            else row_epilogue<EPI>(a, row, acc, own, dv, xs, rh, sq, aux);
+        }
     }
-    if (EPI != EPI_SPMV) {
+    if (EPI != EPI_SPMV && a.acc_out == nullptr) {
         const int kind = EPI == EPI_PUSH ? TAIL_TERM : (EPI == EPI_CG ? TAIL_CG_PAP : TAIL_RESID);
         grid_reduce_and_tail<NT>(sq, aux, a.ctl, a.partials, kind, a.it, a.last_in_iter, a.identity_res, a.defer_tail,
                                  a.norm_log, s_red, &s_flag, &a.px);
@@ -1098,6 +1121,132 @@ int32_t launch_csr_to_sell(const double *vals, const uint32_t *cols, const uint3
     if (grid > 148 * 16) grid = 148 * 16;
     csr_to_sell_kernel<<<grid, 256, 0, stream>>>(vals, cols, row_ptr, nrows, sell_ptr, sell_cols, sell_vals);
     SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// column-slab split at ingest (one-off; matrix.cu build_slabs)
+// ---------------------------------------------------------------------------------------------------------
+struct SlabPtrs {
+    uint32_t *counts[kMaxSlabs];
+    const uint32_t *row_ptr[kMaxSlabs];
+    uint32_t *cols[kMaxSlabs];
+    double *vals[kMaxSlabs];
+};
+
+__global__ void slab_count_kernel(const uint32_t *__restrict__ cols, const uint32_t *__restrict__ row_ptr, uint32_t nrows,
+                                  uint32_t slab_width, int nslabs, SlabPtrs p, int *unsorted) {
+    for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += gridDim.x * blockDim.x) {
+        uint32_t cnt[kMaxSlabs] = {0u, 0u, 0u, 0u};
+        uint32_t prev = 0;
+        bool bad = false;
+        for (uint32_t k = row_ptr[row]; k < row_ptr[row + 1]; k++) {
+            const uint32_t c = cols[k];
+            bad |= c < prev;
+            prev = c;
+            const uint32_t s = min(c / slab_width, (uint32_t)(nslabs - 1));
+            cnt[s]++;
+        }
+        for (int s = 0; s < nslabs; s++) p.counts[s][row] = cnt[s];
+        if (bad) *unsorted = 1;
+    }
+}
+
+__global__ void slab_fill_kernel(const double *__restrict__ vals, const uint32_t *__restrict__ cols,
+                                 const uint32_t *__restrict__ row_ptr, uint32_t nrows, uint32_t slab_width, int nslabs,
+                                 SlabPtrs p) {
+    for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += gridDim.x * blockDim.x) {
+        uint32_t pos[kMaxSlabs];
+        for (int s = 0; s < nslabs; s++) pos[s] = p.row_ptr[s][row];
+        for (uint32_t k = row_ptr[row]; k < row_ptr[row + 1]; k++) {  // in CSR order: the order inside a slab row is kept
+            const uint32_t c = cols[k];
+            const uint32_t s = min(c / slab_width, (uint32_t)(nslabs - 1));
+            p.cols[s][pos[s]] = c;
+            p.vals[s][pos[s]] = vals[k];
+            pos[s]++;
+        }
+    }
+}
+
+int32_t launch_slab_count(const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows, uint32_t slab_width, int nslabs,
+                          uint32_t *const *counts, int *unsorted, cudaStream_t stream) {
+    SlabPtrs p{};
+    for (int s = 0; s < nslabs; s++) p.counts[s] = counts[s];
+    unsigned grid = (nrows + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid == 0) grid = 1;
+    slab_count_kernel<<<grid, 256, 0, stream>>>(cols, row_ptr, nrows, slab_width, nslabs, p, unsorted);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+int32_t launch_slab_fill(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
+                         uint32_t slab_width, int nslabs, const uint32_t *const *slab_row_ptr, uint32_t *const *slab_cols,
+                         double *const *slab_vals, cudaStream_t stream) {
+    SlabPtrs p{};
+    for (int s = 0; s < nslabs; s++) {
+        p.row_ptr[s] = slab_row_ptr[s];
+        p.cols[s] = slab_cols[s];
+        p.vals[s] = slab_vals[s];
+    }
+    unsigned grid = (nrows + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid == 0) grid = 1;
+    slab_fill_kernel<<<grid, 256, 0, stream>>>(vals, cols, row_ptr, nrows, slab_width, nslabs, p);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+// exclusive prefix sum of n u32 counts in place (data has n + 1 entries: data[n] receives the total), single CTA:
+// an ingest-time helper, not a hot path (10 M rows: ~1 ms)
+__global__ void __launch_bounds__(1024) exclusive_scan_u32_kernel(uint32_t *data, uint64_t n, unsigned long long *total) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0ull;
+    __syncthreads();
+    for (uint64_t base = 0; base < n; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long v = i < n ? data[i] : 0ull;
+        unsigned long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned long long before = s_carry + (warp ? s_warp[warp - 1] : 0ull) + (x - v);
+        if (i < n) data[i] = (uint32_t)before;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        data[n] = (uint32_t)s_carry;
+        *total = s_carry;
+    }
+}
+
+int32_t device_exclusive_scan_u32(uint32_t *data, uint64_t n, uint64_t *total, cudaStream_t stream) {
+    DevBuf<unsigned long long> t;
+    SB_TRY(t.alloc(1));
+    exclusive_scan_u32_kernel<<<1, 1024, 0, stream>>>(data, n, t.p);
+    SB_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    SB_CUDA(cudaMemcpyAsync(&h, t.p, 8, cudaMemcpyDeviceToHost, stream));
+    SB_CUDA(cudaStreamSynchronize(stream));
+    if (total) *total = h;
     return SB200_OK;
 }
 

@@ -21,6 +21,11 @@ sb200_matrix::~sb200_matrix() {
     d_sell_ptr.release();
     d_sell_cols.release();
     d_sell_vals.release();
+    for (int s = 0; s < sb200::kMaxSlabs; s++) {
+        d_slab_vals[s].release();
+        d_slab_cols[s].release();
+        d_slab_row_ptr[s].release();
+    }
     d_dinv[0].release();
     d_dinv[1].release();
     if (stream) cudaStreamDestroy(stream);
@@ -137,10 +142,83 @@ static int32_t build_sell(sb200_matrix *m) {
     return SB200_OK;
 }
 
+// Column-slab split for the hot kernels. Measured on a B200 (profiles/r1_slab_timing.log): random 8-byte
+// gathers cost one L2 sector operation while the gather source fits the L2 partition of each die (<= ~40 MB) and 2.4
+// once it does not (80 MB: every far-homed line is looked up near, fetched over the fabric and filled again), and the
+// push kernel runs at the chip's L2 sector-throughput cap. Splitting the columns into slabs of <= 28 MB of the vector and
+// running one pass per slab keeps the gathers at one operation each; rows are column-sorted, so carrying the row sum
+// from slab to slab adds the products in exactly the CSR order.
+// $SUBLINEAR_B200_SLABS = 0 forbids, 2..4 forces that many slabs; default: square matrices whose vector is > 48 MB and
+// <= 4 * 42 MB. Needs every row sorted by column (checked on the device), otherwise the split is dropped.
+static int32_t build_slabs(sb200_matrix *m) {
+    m->nslabs = 0;
+    if (m->tile_cfg >= 0 || m->nrows == 0 || m->nnz == 0) return SB200_OK;
+    const char *e = getenv("SUBLINEAR_B200_SLABS");
+    const int force = e ? atoi(e) : -1;
+    if (force == 0 || force == 1) return SB200_OK;
+    int S = 0;
+    const double vec_bytes = 8.0 * (double)m->ncols;
+    if (force >= 2) {
+        S = force > kMaxSlabs ? kMaxSlabs : force;
+        if ((uint64_t)S > m->ncols) return SB200_OK;
+    } else {
+        if (m->nrows != m->ncols || vec_bytes <= 48e6 || vec_bytes > 4 * 42e6) return SB200_OK;
+        S = (int)std::ceil(vec_bytes / 28e6);
+        if (S > kMaxSlabs) S = kMaxSlabs;
+    }
+    const uint32_t width = (uint32_t)((m->ncols + S - 1) / S);
+    const uint64_t n = m->nrows;
+    DevBuf<int> d_unsorted;
+    SB_TRY(d_unsorted.alloc(1));
+    SB_CUDA(cudaMemsetAsync(d_unsorted.p, 0, sizeof(int), m->stream));
+    uint32_t *counts[kMaxSlabs] = {nullptr, nullptr, nullptr, nullptr};
+    for (int s = 0; s < S; s++) {
+        SB_TRY(m->d_slab_row_ptr[s].alloc(n + 1));
+        counts[s] = m->d_slab_row_ptr[s].p;
+    }
+    SB_TRY(launch_slab_count(m->d_cols.p, m->d_row_ptr.p, (uint32_t)n, width, S, counts, d_unsorted.p, m->stream));
+    int unsorted = 0;
+    SB_CUDA(cudaMemcpyAsync(&unsorted, d_unsorted.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    SB_CUDA(cudaStreamSynchronize(m->stream));
+    auto drop = [&]() {
+        for (int s = 0; s < kMaxSlabs; s++) {
+            m->d_slab_row_ptr[s].release();
+            m->d_slab_cols[s].release();
+            m->d_slab_vals[s].release();
+            m->slab_nnz[s] = 0;
+        }
+    };
+    if (unsorted) {  // from_csr input with unsorted rows: the split would reorder the sums
+        drop();
+        return SB200_OK;
+    }
+    uint32_t *scols[kMaxSlabs] = {nullptr, nullptr, nullptr, nullptr};
+    double *svals[kMaxSlabs] = {nullptr, nullptr, nullptr, nullptr};
+    const uint32_t *srp[kMaxSlabs] = {nullptr, nullptr, nullptr, nullptr};
+    for (int s = 0; s < S; s++) {
+        uint64_t total = 0;
+        SB_TRY(device_exclusive_scan_u32(m->d_slab_row_ptr[s].p, n, &total, m->stream));
+        m->slab_nnz[s] = total;
+        const size_t pad = ((total + 3) & ~(size_t)3) + 8;  // same over-read slack as the CSR slices
+        SB_TRY(m->d_slab_cols[s].alloc(pad));
+        SB_TRY(m->d_slab_vals[s].alloc(pad));
+        SB_CUDA(cudaMemsetAsync(m->d_slab_cols[s].p + total, 0, (pad - total) * sizeof(uint32_t), m->stream));
+        SB_CUDA(cudaMemsetAsync(m->d_slab_vals[s].p + total, 0, (pad - total) * sizeof(double), m->stream));
+        scols[s] = m->d_slab_cols[s].p;
+        svals[s] = m->d_slab_vals[s].p;
+        srp[s] = m->d_slab_row_ptr[s].p;
+    }
+    SB_TRY(launch_slab_fill(m->d_vals.p, m->d_cols.p, m->d_row_ptr.p, (uint32_t)n, width, S, srp, scols, svals, m->stream));
+    SB_CUDA(cudaStreamSynchronize(m->stream));
+    m->nslabs = S;
+    m->slab_width = width;
+    return SB200_OK;
+}
+
 // Upload a validated host CSR. Exactly one of row_ptr64 / row_ptr32 is non-null.
 int32_t matrix_from_host_csr(const uint64_t *row_ptr64, const uint32_t *row_ptr32, const uint32_t *cols,
                              const double *vals, uint64_t nrows, uint64_t ncols, uint64_t nnz, bool validate,
-                             sb200_matrix **out) {
+                             sb200_matrix **out, bool allow_slabs) {
     if (!out) return fail(SB200_ERR_INVALID_INPUT, "out is null");
     *out = nullptr;
     if (nrows >= 0xFFFFFFF0ull || ncols >= 0xFFFFFFF0ull)
@@ -208,7 +286,8 @@ int32_t matrix_from_host_csr(const uint64_t *row_ptr64, const uint32_t *row_ptr3
     SB_TRY(copy_h2d(m->d_cols.p, cols, nnz * sizeof(uint32_t), m->stream));
     SB_TRY(copy_h2d(m->d_row_ptr.p, rp, (nrows + 1) * sizeof(uint32_t), m->stream));
     SB_TRY(copy_h2d(m->d_tiles.p, tiles.data(), tiles.size() * sizeof(TileDesc), m->stream));
-    SB_TRY(build_sell(m.get()));
+    if (allow_slabs) SB_TRY(build_slabs(m.get()));  // row blocks of the multi-GPU path keep the single-pass kernels
+    if (m->nslabs == 0) SB_TRY(build_sell(m.get()));
     SB_CUDA(cudaStreamSynchronize(m->stream));
     *out = m.release();
     return SB200_OK;
@@ -223,6 +302,12 @@ void fill_tile_args(const sb200_matrix *m, TileKernelArgs &a) {
     a.sell_ptr = m->use_sell ? m->d_sell_ptr.p : nullptr;
     a.sell_cols = m->d_sell_cols.p;
     a.sell_vals = m->d_sell_vals.p;
+    a.nslabs = m->nslabs;
+    for (int s = 0; s < m->nslabs; s++) {
+        a.slab_vals[s] = m->d_slab_vals[s].p;
+        a.slab_cols[s] = m->d_slab_cols[s].p;
+        a.slab_row_ptr[s] = m->d_slab_row_ptr[s].p;
+    }
     a.nrows = (uint32_t)m->nrows;
     a.row_base = (uint32_t)m->row_base;
     a.xin_len = m->ncols;
@@ -464,12 +549,16 @@ int32_t sb200_matrix_nnz(const sb200_matrix *m, uint64_t *out) {
 
 int32_t sb200_matrix_storage_info(const sb200_matrix *m, int32_t *layout, uint64_t *slots, uint64_t *device_bytes) {
     if (!m) return fail(SB200_ERR_INVALID_INPUT, "null argument");
-    if (layout) *layout = m->use_sell ? SB200_LAYOUT_SELL32 : SB200_LAYOUT_CSR;
+    if (layout) *layout = m->nslabs > 1 ? SB200_LAYOUT_CSR_SLABS : (m->use_sell ? SB200_LAYOUT_SELL32 : SB200_LAYOUT_CSR);
     if (slots) *slots = m->use_sell ? m->sell_slabs * 32 : m->nnz;
-    if (device_bytes)
-        *device_bytes = m->d_vals.n * 8 + m->d_cols.n * 4 + m->d_row_ptr.n * 4 + m->d_tiles.n * sizeof(TileDesc) +
-                        m->d_sell_ptr.n * 4 + m->d_sell_cols.n * 4 + m->d_sell_vals.n * 8 + m->d_dinv[0].n * 8 +
-                        m->d_dinv[1].n * 8;
+    if (device_bytes) {
+        uint64_t b = m->d_vals.n * 8 + m->d_cols.n * 4 + m->d_row_ptr.n * 4 + m->d_tiles.n * sizeof(TileDesc) +
+                     m->d_sell_ptr.n * 4 + m->d_sell_cols.n * 4 + m->d_sell_vals.n * 8 + m->d_dinv[0].n * 8 +
+                     m->d_dinv[1].n * 8;
+        for (int s = 0; s < kMaxSlabs; s++)
+            b += m->d_slab_vals[s].n * 8 + m->d_slab_cols[s].n * 4 + m->d_slab_row_ptr[s].n * 4;
+        *device_bytes = b;
+    }
     return SB200_OK;
 }
 
@@ -581,6 +670,7 @@ int32_t sb200_matrix_scale(sb200_matrix *m, double factor) {
     DeviceGuard g(m->device);
     SB_TRY(launch_scale(m->d_vals.p, m->nnz, factor, m->stream));
     if (m->use_sell) SB_TRY(launch_scale(m->d_sell_vals.p, m->sell_slabs * 32, factor, m->stream));
+    for (int s = 0; s < m->nslabs; s++) SB_TRY(launch_scale(m->d_slab_vals[s].p, m->slab_nnz[s], factor, m->stream));
     SB_CUDA(cudaStreamSynchronize(m->stream));
     std::lock_guard<std::mutex> lk(m->mu);
     m->analysed[0] = m->analysed[1] = m->col_analysed = false;  // cached D^-1 is stale

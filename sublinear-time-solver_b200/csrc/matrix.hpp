@@ -49,6 +49,15 @@ struct sb200_matrix {
     sb200::DevBuf<double> d_sell_vals;    // sell_slabs * 32
     uint64_t sell_slabs = 0;
     bool use_sell = false;
+    // column-slab split for the hot kernels (kernels.cu launch_tile_kernel): when the gather source (8 * ncols bytes) does
+    // not fit the L2 partition of a die, the entries are regrouped into nslabs column ranges of slab_width columns, each
+    // with its own CSR slices; one kernel pass per slab, row sums carried over in column order (bit-identical results)
+    int nslabs = 0;
+    uint32_t slab_width = 0;
+    sb200::DevBuf<double> d_slab_vals[sb200::kMaxSlabs];
+    sb200::DevBuf<uint32_t> d_slab_cols[sb200::kMaxSlabs];
+    sb200::DevBuf<uint32_t> d_slab_row_ptr[sb200::kMaxSlabs];
+    uint64_t slab_nnz[sb200::kMaxSlabs] = {0, 0, 0, 0};
     cudaStream_t stream = nullptr;  // for host-pointer entry points
 
     // distributed: this handle holds rows [row_base, row_base + nrows) of an n_global-square system
@@ -76,7 +85,7 @@ namespace sb200 {
 // ingest helpers (matrix.cu)
 int32_t matrix_from_host_csr(const uint64_t *row_ptr64, const uint32_t *row_ptr32, const uint32_t *cols,
                              const double *vals, uint64_t nrows, uint64_t ncols, uint64_t nnz, bool validate,
-                             sb200_matrix **out);
+                             sb200_matrix **out, bool allow_slabs = true);
 int32_t matrix_analyse(sb200_matrix *m, int mode, bool need_cols);
 int32_t matrix_spmv_dev(const sb200_matrix *m, const double *x_dev, double *y_dev, int accumulate, cudaStream_t st);
 void matrix_retain(sb200_matrix *m);

@@ -59,6 +59,7 @@ int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev
     SB_CUDA(cudaMemcpyAsync(ws.ctl.p, ws.h_ctl, sizeof(LoopCtl), cudaMemcpyHostToDevice, st));
 
     uint64_t launches = 0, extra_matvec = 0;
+    const uint64_t kpl = m->nslabs > 1 ? (uint64_t)m->nslabs : 1;  // kernel launches per pass over the matrix
     const double *dinv = m->d_dinv[opt->mode].p;
     const double *resid_rhs = compat ? ws.c.p : b_dev;  // update_residual subtracts D^-1 b in the reference (:308-314)
 
@@ -66,7 +67,7 @@ int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev
     const double *ax0 = nullptr;
     if (!compat && x0_dev) {
         SB_TRY(matrix_spmv_dev(m, x0_dev, ws.tmp.p, 0, st));
-        launches++;
+        launches += kpl;
         extra_matvec++;
         ax0 = ws.tmp.p;
     }
@@ -76,6 +77,7 @@ int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev
     base.ctl = ws.ctl.p;
     base.partials = ws.partials.p;
     base.identity_res = identity;
+    base.acc = ws.tmp.p;  // column-slab passes: partial row sums (A x0, the only other use of tmp, is consumed by the init kernel)
 
     // optional per-launch events (options.enable_profiling): which launches did work is known after the loop
     struct ProfEv {
@@ -116,7 +118,7 @@ int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev
         a.last_in_iter = last;
         a.force = force;
         a.identity_res = 0;
-        launches++;
+        launches += kpl;
         SB_TRY(prof_begin(2, it, force));
         SB_TRY(launch_tile_kernel(cfg, EPI_RESID, a, st));
         return prof_end();
@@ -209,7 +211,7 @@ int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev
                 SB_TRY(prof_begin(1, it, 0));
                 SB_TRY(launch_tile_kernel(cfg, EPI_PUSH, a, st));
                 SB_TRY(prof_end());
-                launches++;
+                launches += kpl;
                 if (resid_due) SB_TRY(enqueue_resid(it, 1, 0));
             }
             SB_TRY(read_ctl());
@@ -608,6 +610,7 @@ int32_t sb200_push_iterations_dev(const sb200_matrix *m, const double *b_dev, ui
     fill_tile_args(m, base);
     base.ctl = ws->ctl.p;
     base.partials = ws->partials.p;
+    base.acc = ws->tmp.p;
     base.force = 1;
     base.norm_log = ws->norm_log.p;
     base.sol = x;

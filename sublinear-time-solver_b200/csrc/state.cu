@@ -174,6 +174,7 @@ int32_t sb200_state_step(sb200_state *st, int32_t *step_result) {
             fill_tile_args(m, a);
             a.ctl = ws.ctl.p;
             a.partials = ws.partials.p;
+            a.acc = ws.tmp.p;
             a.xin = ws.t[st->cur].p;
             a.xin_own = a.xin;
             a.out = ws.t[st->cur ^ 1].p;
@@ -192,6 +193,7 @@ int32_t sb200_state_step(sb200_state *st, int32_t *step_result) {
         fill_tile_args(m, a);
         a.ctl = ws.ctl.p;
         a.partials = ws.partials.p;
+        a.acc = ws.tmp.p;
         a.xin = ws.x.p;
         a.xin_own = a.xin;
         a.rhs = compat ? ws.c.p : ws.b.p;

@@ -28,7 +28,7 @@ MODE_CORRECT, MODE_REF_COMPAT = 0, 1
 DOMINANCE_ROW, DOMINANCE_ROW_OR_COL = 0, 1
 RESIDUAL_EVERY_5, RESIDUAL_IDENTITY = 0, 1
 DUP_KEEP, DUP_SUM = 0, 1
-LAYOUT_CSR, LAYOUT_SELL32 = 0, 1
+LAYOUT_CSR, LAYOUT_SELL32, LAYOUT_CSR_SLABS = 0, 1, 2
 STEP_CONTINUE, STEP_CONVERGED = 0, 1
 UNIQUE_ID_BYTES = 128
 
@@ -448,7 +448,8 @@ class SparseMatrix:
         _check(lib().sb200_matrix_scale(self._h, factor))
 
     def storage_info(self):
-        """Device layout the hot kernels read: {'layout': LAYOUT_CSR | LAYOUT_SELL32, 'slots', 'device_bytes'}."""
+        """Device layout the hot kernels read: {'layout': LAYOUT_CSR | LAYOUT_SELL32 | LAYOUT_CSR_SLABS, 'slots',
+        'device_bytes'}."""
         lay, slots, nbytes = C.c_int32(), C.c_uint64(), C.c_uint64()
         _check(lib().sb200_matrix_storage_info(self._h, C.byref(lay), C.byref(slots), C.byref(nbytes)))
         return {"layout": lay.value, "slots": slots.value, "device_bytes": nbytes.value}
