@@ -217,6 +217,8 @@ def main():
     dist = world > 1
     if dist:
         import torch.distributed as td
+        # stdout carries ONE JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     size, sparsity = WORKLOADS[args.workload]

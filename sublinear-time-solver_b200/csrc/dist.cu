@@ -244,6 +244,7 @@ int32_t push_iterations_p2p(sb200_comm *c, sb200_matrix *mm, const DistPlan &p, 
     fill_tile_args(mm, base);
     base.ctl = ws.ctl.p;
     base.partials = ws.partials.p;
+    base.acc = ws.tmp.p;  // column-slab passes: partial row sums
     base.force = 1;
     base.sol = x;
     base.dinv = mm->d_dinv[0].p;
@@ -334,7 +335,7 @@ int32_t sb200_dist_matrix_from_csr(sb200_comm *c, uint64_t n_global, uint64_t ro
                     (unsigned long long)e0, (unsigned long long)e1, (unsigned long long)row0, (unsigned long long)row1);
     SB_TRY(sb200_set_device(c->device));
     const uint64_t nloc = row1 - row0;
-    SB_TRY(matrix_from_host_csr(row_ptr, nullptr, col_indices, values, nloc, n_global, row_ptr[nloc], true, out, false));
+    SB_TRY(matrix_from_host_csr(row_ptr, nullptr, col_indices, values, nloc, n_global, row_ptr[nloc], true, out));
     (*out)->distributed = true;
     (*out)->tile_cfg = -1;  // the fused exchange lives in the warp-stream kernel
     (*out)->row_base = row0;
@@ -399,6 +400,7 @@ int32_t sb200_dist_push_iterations_dev(sb200_comm *c, const sb200_matrix *m, con
     fill_tile_args(m, base);
     base.ctl = ws->ctl.p;
     base.partials = ws->partials.p;
+    base.acc = ws->tmp.p;
     base.force = 1;
     base.sol = x;
     base.dinv = m->d_dinv[0].p;
@@ -497,6 +499,7 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
     fill_tile_args(m, base);
     base.ctl = ws->ctl.p;
     base.partials = ws->partials.p;
+    base.acc = ws->tmp.p;
     base.identity_res = identity;
     base.defer_tail = multi && !p2p;
 

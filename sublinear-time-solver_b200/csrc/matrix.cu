@@ -148,8 +148,8 @@ static int32_t build_sell(sb200_matrix *m) {
 // push kernel runs at the chip's L2 sector-throughput cap. Splitting the columns into slabs of <= 28 MB of the vector and
 // running one pass per slab keeps the gathers at one operation each; rows are column-sorted, so carrying the row sum
 // from slab to slab adds the products in exactly the CSR order.
-// $SUBLINEAR_B200_SLABS = 0 forbids, 2..4 forces that many slabs; default: square matrices whose vector is > 48 MB and
-// <= 4 * 42 MB. Needs every row sorted by column (checked on the device), otherwise the split is dropped.
+// $SUBLINEAR_B200_SLABS = 0 forbids, 2..4 forces that many slabs; default: matrices (and the row blocks of the multi-GPU
+// path, whose gather source is the full-length vector) whose gathered vector is > 48 MB and <= 4 * 42 MB. Needs every row sorted by column (checked on the device), otherwise the split is dropped.
 static int32_t build_slabs(sb200_matrix *m) {
     m->nslabs = 0;
     if (m->tile_cfg >= 0 || m->nrows == 0 || m->nnz == 0) return SB200_OK;
@@ -162,7 +162,7 @@ static int32_t build_slabs(sb200_matrix *m) {
         S = force > kMaxSlabs ? kMaxSlabs : force;
         if ((uint64_t)S > m->ncols) return SB200_OK;
     } else {
-        if (m->nrows != m->ncols || vec_bytes <= 48e6 || vec_bytes > 4 * 42e6) return SB200_OK;
+        if (vec_bytes <= 48e6 || vec_bytes > 4 * 42e6) return SB200_OK;
         S = (int)std::ceil(vec_bytes / 28e6);
         if (S > kMaxSlabs) S = kMaxSlabs;
     }
@@ -286,7 +286,7 @@ int32_t matrix_from_host_csr(const uint64_t *row_ptr64, const uint32_t *row_ptr3
     SB_TRY(copy_h2d(m->d_cols.p, cols, nnz * sizeof(uint32_t), m->stream));
     SB_TRY(copy_h2d(m->d_row_ptr.p, rp, (nrows + 1) * sizeof(uint32_t), m->stream));
     SB_TRY(copy_h2d(m->d_tiles.p, tiles.data(), tiles.size() * sizeof(TileDesc), m->stream));
-    if (allow_slabs) SB_TRY(build_slabs(m.get()));  // row blocks of the multi-GPU path keep the single-pass kernels
+    if (allow_slabs) SB_TRY(build_slabs(m.get()));
     if (m->nslabs == 0) SB_TRY(build_sell(m.get()));
     SB_CUDA(cudaStreamSynchronize(m->stream));
     *out = m.release();
