@@ -194,8 +194,9 @@ struct SetupOut {
 };
 int32_t launch_setup_rows(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
                           uint32_t row_base, int compat_diag, SetupOut out, cudaStream_t stream);
-// column-slab split at ingest: counts per (row, slab), then the ordered fill; `unsorted` receives 1 if some row is not
-// sorted by column (then the split would change the accumulation order and is not used)
+// column-slab split at ingest: counts per (row, slab), then the ordered fill; unsorted[0] receives 1 if some row is not
+// sorted by column (then the split would change the accumulation order and is not used), unsorted[1] the number of
+// rows whose entries fall into more than one slab
 int32_t launch_slab_count(const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows, uint32_t slab_width, int nslabs,
                           uint32_t *const *counts, int *unsorted, cudaStream_t stream);
 int32_t launch_slab_fill(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,

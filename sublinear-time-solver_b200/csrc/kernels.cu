@@ -1147,8 +1147,13 @@ __global__ void slab_count_kernel(const uint32_t *__restrict__ cols, const uint3
             const uint32_t s = min(c / slab_width, (uint32_t)(nslabs - 1));
             cnt[s]++;
         }
-        for (int s = 0; s < nslabs; s++) p.counts[s][row] = cnt[s];
-        if (bad) *unsorted = 1;
+        int used = 0;
+        for (int s = 0; s < nslabs; s++) {
+            p.counts[s][row] = cnt[s];
+            used += cnt[s] != 0u;
+        }
+        if (bad) unsorted[0] = 1;
+        if (used > 1) atomicAdd(unsorted + 1, 1);  // rows whose gathers spread over several slabs
     }
 }
 

@@ -169,17 +169,21 @@ static int32_t build_slabs(sb200_matrix *m) {
     const uint32_t width = (uint32_t)((m->ncols + S - 1) / S);
     const uint64_t n = m->nrows;
     DevBuf<int> d_unsorted;
-    SB_TRY(d_unsorted.alloc(1));
-    SB_CUDA(cudaMemsetAsync(d_unsorted.p, 0, sizeof(int), m->stream));
+    SB_TRY(d_unsorted.alloc(2));
+    SB_CUDA(cudaMemsetAsync(d_unsorted.p, 0, 2 * sizeof(int), m->stream));
     uint32_t *counts[kMaxSlabs] = {nullptr, nullptr, nullptr, nullptr};
     for (int s = 0; s < S; s++) {
         SB_TRY(m->d_slab_row_ptr[s].alloc(n + 1));
         counts[s] = m->d_slab_row_ptr[s].p;
     }
     SB_TRY(launch_slab_count(m->d_cols.p, m->d_row_ptr.p, (uint32_t)n, width, S, counts, d_unsorted.p, m->stream));
-    int unsorted = 0;
-    SB_CUDA(cudaMemcpyAsync(&unsorted, d_unsorted.p, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    int flags[2] = {0, 0};
+    SB_CUDA(cudaMemcpyAsync(flags, d_unsorted.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     SB_CUDA(cudaStreamSynchronize(m->stream));
+    const int unsorted = flags[0];
+    // banded / block-local matrices gather from a window of the vector that stays cached anyway: extra passes would
+    // only add row_ptr and partial-sum traffic. Split only when most rows really reach into several slabs.
+    const bool local = force < 2 && (uint64_t)flags[1] * 2 < n;
     auto drop = [&]() {
         for (int s = 0; s < kMaxSlabs; s++) {
             m->d_slab_row_ptr[s].release();
@@ -188,7 +192,7 @@ static int32_t build_slabs(sb200_matrix *m) {
             m->slab_nnz[s] = 0;
         }
     };
-    if (unsorted) {  // from_csr input with unsorted rows: the split would reorder the sums
+    if (unsorted || local) {  // unsorted rows (from_csr input): the split would reorder the sums
         drop();
         return SB200_OK;
     }
