@@ -134,6 +134,8 @@ struct PeerExchange {               // all zero = not used (single GPU, or the N
 };
 
 constexpr int kMaxSlabs = 4;  // column slabs of the gather source (matrix.cu build_slabs)
+constexpr uint32_t kLongRow = 1024;    // rows above this length leave the ordered per-lane sums (warp-stream kernel)
+constexpr uint32_t kLongChunk = 8192;  // entries of a long row summed by one CTA of the pre-pass
 
 enum Epilogue { EPI_SPMV = 0, EPI_PUSH = 1, EPI_RESID = 2, EPI_CG = 3 };  // EPI_CG: out = A p and sum p_i (A p)_i (warp-stream kernel only)
 
@@ -155,6 +157,14 @@ struct TileKernelArgs {
     const double *slab_vals[kMaxSlabs];
     const uint32_t *slab_cols[kMaxSlabs];
     const uint32_t *slab_row_ptr[kMaxSlabs];
+    // rows with more than kLongRow entries (hub rows of power-law graphs): launch_tile_kernel lets the whole grid compute
+    // their sums first (kernels.cu long_rows_*), the row-block kernel only looks them up
+    uint32_t nlong;             // number of long rows of this matrix (0: none)
+    uint32_t nlong_chunks;
+    const uint32_t *long_rows;  // their local row ids, ascending
+    const uint32_t *long_first; // nlong + 1: first chunk of every long row
+    const uint2 *long_chunks;   // {begin, end} entry ranges of at most kLongChunk entries
+    const double *long_sum;     // set by the launcher: (A xin)_row of the long rows, in list order
     double *acc;           // n doubles of scratch for the partial row sums; null: `out` carries them
     const double *acc_in;  // set per pass by the launcher: continue these sums (null in the first pass)
     double *acc_out;       // set per pass by the launcher: store the sums instead of running the epilogue (null in the last)

@@ -106,6 +106,28 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t *p) {
     return v;
 }
 
+// streaming (use-once) accesses with an explicit L2 policy
+__device__ __forceinline__ uint32_t ld_stream_u32_hint(const uint32_t *p, uint64_t policy) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ double ld_stream_f64_hint(const double *p, uint64_t policy) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+    return v;
+}
+
+// the same for memory that this kernel also writes (the carried row sums): no .nc
+__device__ __forceinline__ double ld_once_f64_hint(const double *p, uint64_t policy) {
+    double v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_stream_f64_hint(double *p, double v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // deterministic reductions + device-side loop control
 // ---------------------------------------------------------------------------------------------------------
@@ -647,6 +669,50 @@ static int32_t launch_warp_any(Epilogue epi, const TileKernelArgs &a, cudaStream
 
 static int32_t launch_sell_any(Epilogue epi, const TileKernelArgs &a, cudaStream_t stream, int *mg);
 
+// ---------------------------------------------------------------------------------------------------------
+// hub rows: a row with millions of entries must not be left to one warp (measured: 470 ms per SpMV for a PageRank
+// system with a 2 M-entry row). Ingest lists the rows above kLongRow entries and cuts them into chunks of kLongChunk;
+// before the row-block kernel, one CTA per chunk forms a partial sum (coalesced stream loads, lane-strided order +
+// fixed tree) and one thread per row adds the row's partials in order. Tolerance-level parity, as for every long row.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) long_rows_chunk_kernel(const TileKernelArgs a, double *partial, int check_alive) {
+    __shared__ double s_red[8];
+    if (check_alive && a.ctl->alive == 0) return;  // loop already finished: no-op launch
+    const uint64_t pol_gather = policy_evict_last();
+    for (uint32_t c = blockIdx.x; c < a.nlong_chunks; c += gridDim.x) {
+        const uint2 r = a.long_chunks[c];
+        double part = 0.0;
+        for (uint32_t k = r.x + threadIdx.x; k < r.y; k += 256u)
+            part += ld_stream_f64(a.vals + k) * ld_gather(a.xin + ld_stream_u32(a.cols + k), pol_gather);
+        part = block_sum<256>(part, s_red);
+        if (threadIdx.x == 0) partial[c] = part;
+    }
+}
+
+__global__ void long_rows_combine_kernel(const TileKernelArgs a, const double *partial, double *sum, int check_alive) {
+    if (check_alive && a.ctl->alive == 0) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.nlong; i += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (uint32_t c = a.long_first[i]; c < a.long_first[i + 1u]; c++) s += partial[c];
+        sum[i] = s;
+    }
+}
+
+static int32_t launch_with_long_rows(Epilogue epi, const TileKernelArgs &a, cudaStream_t stream) {
+    double *scratch = nullptr;  // per launch, stream ordered: concurrent solves on one matrix handle do not share it
+    SB_CUDA(cudaMallocAsync((void **)&scratch, ((size_t)a.nlong_chunks + a.nlong) * sizeof(double), stream));
+    const int check_alive = epi != EPI_SPMV && !a.force;
+    const unsigned grid = a.nlong_chunks < 148u * 8u ? a.nlong_chunks : 148u * 8u;
+    long_rows_chunk_kernel<<<grid, 256, 0, stream>>>(a, scratch, check_alive);
+    long_rows_combine_kernel<<<(a.nlong + 127u) / 128u, 128, 0, stream>>>(a, scratch, scratch + a.nlong_chunks, check_alive);
+    TileKernelArgs p = a;
+    p.long_sum = scratch + a.nlong_chunks;
+    int32_t rc = cudaGetLastError() == cudaSuccess ? SB200_OK : fail(SB200_ERR_ALGORITHM, "long-row pre-pass launch failed");
+    if (rc == SB200_OK) rc = launch_warp_any(epi, p, stream, nullptr);
+    cudaFreeAsync(scratch, stream);
+    return rc;
+}
+
 int32_t launch_tile_kernel(int cfg, Epilogue epi, const TileKernelArgs &a, cudaStream_t stream) {
     if (cfg < 0 && a.nslabs > 1) {
         // column-slab passes: the gather source of one pass is a slab of the vector small enough to stay in the L2
@@ -666,6 +732,7 @@ int32_t launch_tile_kernel(int cfg, Epilogue epi, const TileKernelArgs &a, cudaS
         return SB200_OK;
     }
     if (cfg < 0 && a.sell_ptr != nullptr) return launch_sell_any(epi, a, stream, nullptr);
+    if (cfg < 0 && a.nlong > 0) return launch_with_long_rows(epi, a, stream);
     if (cfg < 0) return launch_warp_any(epi, a, stream, nullptr);
     if (epi == EPI_CG) return fail(SB200_ERR_INVALID_INPUT, "the CG epilogue exists in the warp-stream kernel only");
     if (reinterpret_cast<uintptr_t>(a.xin) & 15u)  // 16-byte gathers and the TMA window copy
@@ -754,7 +821,6 @@ __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
     static_assert(EPL == 4 || EPL == 8, "elements per lane and chunk");
     constexpr int WARPS = NT / 32;
     constexpr uint32_t CH = 32 * EPL;    // elements per chunk: EPL per lane (4: default, 8: twice the gathers in flight)
-    constexpr uint32_t kLongRow = 1024;  // a block holding a longer row falls back to warp-per-row sums
     __shared__ __align__(16) double s_prod[WARPS][CH];
     __shared__ double s_red[WARPS];
     __shared__ int s_flag;
@@ -785,7 +851,7 @@ __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
         // row sums on through acc_out -> acc_in; the order of the additions is the single-pass order
         if (active && (a.acc_out == nullptr || (EPI == EPI_SPMV && a.acc_in == nullptr))) row_operands<EPI>(a, row, own, dv, xs, rh);
         double acc = (EPI == EPI_SPMV && a.accumulate) ? xs : 0.0;
-        if (a.acc_in != nullptr) acc = active ? a.acc_in[row] : 0.0;
+        if (a.acc_in != nullptr) acc = active ? ld_once_f64_hint(a.acc_in + row, pol_stream) : 0.0;  // used once: evict first
         const uint32_t max_len = __reduce_max_sync(0xffffffffu, re - rs);
         if (max_len <= kLongRow) {
             for (uint32_t c0 = b0 & ~(uint32_t)(EPL - 1); c0 < b1; c0 += CH) {
@@ -839,14 +905,26 @@ __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
             for (uint32_t i = 0; i < nr; i++) {
                 const uint32_t s = __shfl_sync(0xffffffffu, rs, (int)i), t = __shfl_sync(0xffffffffu, re, (int)i);
                 double part = 0.0;
-                for (uint32_t k = s + lane; k < t; k += 32u)
-                    part += ld_stream_f64(a.vals + k) * ld_gather(a.xin + ld_stream_u32(a.cols + k), pol_gather);
-                part = warp_sum(part);
+                if (a.long_sum != nullptr && t - s > kLongRow) {
+                    // a hub row: its sum was computed by the whole grid before this launch (long_rows_* below);
+                    // every lane finds the row's slot in the ascending list of long rows
+                    const uint32_t target = row_first + i;
+                    uint32_t lo = 0, hi = a.nlong;
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (a.long_rows[mid] < target) lo = mid + 1; else hi = mid;
+                    }
+                    part = a.long_sum[lo];
+                } else {
+                    for (uint32_t k = s + lane; k < t; k += 32u)
+                        part += ld_stream_f64(a.vals + k) * ld_gather(a.xin + ld_stream_u32(a.cols + k), pol_gather);
+                    part = warp_sum(part);
+                }
                 if ((uint32_t)lane == i) acc += part;
             }
         }
         if (active) {
-            if (a.acc_out != nullptr) a.acc_out[row] = acc;
+            if (a.acc_out != nullptr) st_stream_f64_hint(a.acc_out + row, acc, pol_stream);  // keep the slab of x in L2
             else row_epilogue<EPI>(a, row, acc, own, dv, xs, rh, sq, aux);
         }
     }
@@ -924,17 +1002,6 @@ static int32_t launch_warp_any(Epilogue epi, const TileKernelArgs &a, cudaStream
 //     the last CTA (elected with __syncthreads_or, no shared flag).
 // Padding slots hold value 0 / column 0 and are never gathered or added (k < row length), so non-finite x entries
 // cannot leak into other rows.
-__device__ __forceinline__ uint32_t ld_stream_u32_hint(const uint32_t *p, uint64_t policy) {
-    uint32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
-    return v;
-}
-__device__ __forceinline__ double ld_stream_f64_hint(const double *p, uint64_t policy) {
-    double v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
-    return v;
-}
-
 // warp partial -> global partial array -> warp 0 of the last CTA sums all partials in index order. No shared memory.
 template <int NT>
 __device__ __forceinline__ void grid_reduce_and_tail_regs(double sq, double aux, LoopCtl *ctl, double *partials, int kind,

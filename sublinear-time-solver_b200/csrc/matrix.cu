@@ -21,6 +21,9 @@ sb200_matrix::~sb200_matrix() {
     d_sell_ptr.release();
     d_sell_cols.release();
     d_sell_vals.release();
+    d_long_rows.release();
+    d_long_first.release();
+    d_long_chunks.release();
     for (int s = 0; s < sb200::kMaxSlabs; s++) {
         d_slab_vals[s].release();
         d_slab_cols[s].release();
@@ -142,6 +145,35 @@ static int32_t build_sell(sb200_matrix *m) {
     return SB200_OK;
 }
 
+// Hub rows: rows with more than kLongRow entries get a chunk table so that the whole grid can sum them before the
+// row-block kernel runs (kernels.cu long_rows_*). O(n) over the host row_ptr copy.
+static int32_t build_long_rows(sb200_matrix *m) {
+    m->nlong = m->nlong_chunks = 0;
+    const uint32_t *rp = m->h_row_ptr.data();
+    std::vector<uint32_t> rows, first;
+    std::vector<uint2> chunks;
+    for (uint64_t r = 0; r < m->nrows; r++) {
+        const uint32_t rs = rp[r], re = rp[r + 1];
+        if (re - rs <= kLongRow) continue;
+        rows.push_back((uint32_t)r);
+        first.push_back((uint32_t)chunks.size());
+        for (uint64_t s = rs; s < re; s += kLongChunk)
+            chunks.push_back(make_uint2((uint32_t)s, (uint32_t)std::min<uint64_t>(s + kLongChunk, re)));
+    }
+    if (rows.empty()) return SB200_OK;
+    first.push_back((uint32_t)chunks.size());
+    SB_TRY(m->d_long_rows.alloc(rows.size()));
+    SB_TRY(m->d_long_first.alloc(first.size()));
+    SB_TRY(m->d_long_chunks.alloc(chunks.size()));
+    SB_TRY(copy_h2d(m->d_long_rows.p, rows.data(), rows.size() * sizeof(uint32_t), m->stream));
+    SB_TRY(copy_h2d(m->d_long_first.p, first.data(), first.size() * sizeof(uint32_t), m->stream));
+    SB_TRY(copy_h2d(m->d_long_chunks.p, chunks.data(), chunks.size() * sizeof(uint2), m->stream));
+    SB_CUDA(cudaStreamSynchronize(m->stream));
+    m->nlong = (uint32_t)rows.size();
+    m->nlong_chunks = (uint32_t)chunks.size();
+    return SB200_OK;
+}
+
 // Column-slab split for the hot kernels. Measured on a B200 (profiles/r1_slab_timing.log): random 8-byte
 // gathers cost one L2 sector operation while the gather source fits the L2 partition of each die (<= ~40 MB) and 2.4
 // once it does not (80 MB: every far-homed line is looked up near, fetched over the fabric and filled again), and the
@@ -153,6 +185,7 @@ static int32_t build_sell(sb200_matrix *m) {
 static int32_t build_slabs(sb200_matrix *m) {
     m->nslabs = 0;
     if (m->tile_cfg >= 0 || m->nrows == 0 || m->nnz == 0) return SB200_OK;
+    if (m->nlong > 0) return SB200_OK;  // hub rows are summed by the single-pass pre-pass (per-slab chunk tables: not yet)
     const char *e = getenv("SUBLINEAR_B200_SLABS");
     const int force = e ? atoi(e) : -1;
     if (force == 0 || force == 1) return SB200_OK;
@@ -290,6 +323,7 @@ int32_t matrix_from_host_csr(const uint64_t *row_ptr64, const uint32_t *row_ptr3
     SB_TRY(copy_h2d(m->d_cols.p, cols, nnz * sizeof(uint32_t), m->stream));
     SB_TRY(copy_h2d(m->d_row_ptr.p, rp, (nrows + 1) * sizeof(uint32_t), m->stream));
     SB_TRY(copy_h2d(m->d_tiles.p, tiles.data(), tiles.size() * sizeof(TileDesc), m->stream));
+    SB_TRY(build_long_rows(m.get()));
     if (allow_slabs) SB_TRY(build_slabs(m.get()));
     if (m->nslabs == 0) SB_TRY(build_sell(m.get()));
     SB_CUDA(cudaStreamSynchronize(m->stream));
@@ -306,6 +340,12 @@ void fill_tile_args(const sb200_matrix *m, TileKernelArgs &a) {
     a.sell_ptr = m->use_sell ? m->d_sell_ptr.p : nullptr;
     a.sell_cols = m->d_sell_cols.p;
     a.sell_vals = m->d_sell_vals.p;
+    a.nlong = m->nlong;
+    a.nlong_chunks = m->nlong_chunks;
+    a.long_rows = m->d_long_rows.p;
+    a.long_first = m->d_long_first.p;
+    a.long_chunks = m->d_long_chunks.p;
+    a.long_sum = nullptr;
     a.nslabs = m->nslabs;
     for (int s = 0; s < m->nslabs; s++) {
         a.slab_vals[s] = m->d_slab_vals[s].p;

@@ -49,6 +49,10 @@ struct sb200_matrix {
     sb200::DevBuf<double> d_sell_vals;    // sell_slabs * 32
     uint64_t sell_slabs = 0;
     bool use_sell = false;
+    // hub rows (> kLongRow entries): list + chunk table for the pre-pass of launch_tile_kernel (kernels.cu long_rows_*)
+    uint32_t nlong = 0, nlong_chunks = 0;
+    sb200::DevBuf<uint32_t> d_long_rows, d_long_first;
+    sb200::DevBuf<uint2> d_long_chunks;
     // column-slab split for the hot kernels (kernels.cu launch_tile_kernel): when the gather source (8 * ncols bytes) does
     // not fit the L2 partition of a die, the entries are regrouped into nslabs column ranges of slab_width columns, each
     // with its own CSR slices; one kernel pass per slab, row sums carried over in column order (bit-identical results)
