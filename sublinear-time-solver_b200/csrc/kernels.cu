@@ -1,28 +1,32 @@
 // kernels.cu — the sm_100a kernels of the push-iteration path.
 //
-// One kernel template does every pass over the CSR store; what differs is the per-row epilogue:
+// One kernel body does every pass over the matrix; what differs is the per-row epilogue (row_epilogue below):
 //   EPI_SPMV  : y = A x                      Matrix::multiply_vector        (ref src/matrix/sparse.rs:187-203)
 //   EPI_PUSH  : t' = t - D^-1 (A t); x += t'; ||t'||^2     apply_iteration_matrix + accumulate + l2_norm
 //                                            (ref src/solver/neumann.rs:280-299, 264-266, 271)
 //   EPI_RESID : ||A x - rhs||^2               update_residual               (ref src/solver/neumann.rs:302-318)
+//   EPI_CG    : ap = A p, p.ap                the SpMV + dot of OptimizedConjugateGradientSolver::solve
+//                                            (ref src/optimized_solver.rs:224-232)
 //
-// B200 mapping (HBM-bound sparse gather-reduce; tensor cores are irrelevant here):
-//   * rows are grouped on the host into TILES of <= NT rows and <= CAP non-zeros (CSR-adaptive style);
-//     a persistent grid (multiple of the SM count) walks the tile list.
-//   * the tile's contiguous slices of `values` (f64) and `col_indices` (u32) are streamed HBM -> shared
-//     memory by the TMA engine as 1-D bulk copies (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP),
-//     double-buffered, with an L2 evict_first policy: the 12 B/nnz stream never occupies LSU/L1 issue slots
-//     and does not push the gather source out of L2.
-//   * all NT threads then gather x[col] (L2 evict_last policy: the 8n-byte term vector is the only data
-//     with reuse) and overwrite the staged value with the product, in place.
-//   * one thread per row sums its products left to right, exactly the reference's accumulation order, with
-//     FMA contraction disabled (-fmad=false) so a row sum is bit-identical to CSRStorage::multiply_vector.
-//   * the epilogue (diagonal scale, term/solution update, squared norm) is fused; norms are reduced
-//     deterministically (fixed-shape tree per CTA, fixed-order sum of CTA partials by the last CTA) and
-//     the last CTA also advances the device-resident loop state (LoopCtl), so the host never has to
-//     synchronise per term.
-//   * a row with more than CAP non-zeros is a tile of its own and is streamed with coalesced loads by the
-//     whole CTA (lane-strided partial sums + tree: order differs from the reference, tolerance-level only).
+// B200 mapping (HBM / L2-bound sparse gather-reduce; tensor cores are irrelevant here). Three bodies, all of which add
+// the products of a row LEFT TO RIGHT — the reference's order — with FMA contraction off, so results are bit-identical
+// to CSRStorage::multiply_vector and to each other:
+//   * sell_kernel : SELL-32 copy of the matrix, lane r owns row r of a 32-row block, no shared memory at all
+//                   (the whole 256 KB array serves as L1 for the in-flight gathers); default for vectors <= 48 MB and
+//                   band-local matrices;
+//   * warp_kernel : CSR slices, coalesced 128/256-bit stream loads by the warp, products transposed through a 1 KB
+//                   warp-private shared-memory chunk; used for ragged / power-law rows and as the body of the
+//   * column-slab passes (launch_tile_kernel): when the gathered vector does not fit the L2 partition of a die, one
+//                   warp_kernel pass per <= 28 MB slab of the vector, the running row sums handed from pass to pass
+//                   (2.4 -> 1.07 L2 sector operations per gather);
+//   * tile_kernel : TMA-staged tile pipeline (cp.async.bulk + mbarrier, LDGSTS gathers), kept selectable
+//                   ($SUBLINEAR_B200_TILE_CFG) as the record of what was measured;
+//   * long_rows_* : grid-wide pre-pass for hub rows (> 1024 entries) of power-law graphs.
+// The stream (values, column indices) is read with L1::no_allocate + L2 evict_first, the gathered vector with L2
+// evict_last (a persisting-L2 set-aside is reserved once per device). The epilogue (diagonal scale, term / solution
+// update, squared norm) is fused; norms are reduced deterministically (fixed-shape tree per CTA or warp, fixed-order
+// sum of the partials by the last CTA) and the last CTA also advances the device-resident loop state (LoopCtl), so the
+// host never has to synchronise per term.
 #include "common.hpp"
 
 namespace sb200 {
@@ -984,7 +988,7 @@ static int32_t launch_warp_any(Epilogue epi, const TileKernelArgs &a, cudaStream
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// the SELL-32 kernel (default whenever the padded layout costs <= 25 % extra slots, see matrix.cu)
+// the SELL-32 kernel (vectors <= 48 MB and band-local matrices, when the padded layout costs <= 25 % extra slots)
 // ---------------------------------------------------------------------------------------------------------
 // Measured on the warp-stream kernel (profiles/r1_warp_probe_phases.log): on uniform-random columns the x[col] gathers
 // alone cost 687 us of the 808 us launch although the same gathers run at 265-287 G/s (350-377 us) in isolation. The
