@@ -344,6 +344,53 @@ int32_t sb200_cg_solve_dev(const sb200_matrix *m, const double *b_dev, uint64_t 
 void sb200_cg_result_free(sb200_cg_result *r);
 
 /* ---------------------------------------------------------------------------------------------- */
+/* forward / backward push                                                      */
+/* ---------------------------------------------------------------------------------------------- */
+/* PushGraph (src/graph/adjacency.rs:199-277): adjacency + transpose + out-/in-degrees (row / column weight sums). */
+typedef struct sb200_push_graph sb200_push_graph;
+/* ForwardPushConfig = BackwardPushConfig (src/solver/forward_push.rs:25-50, backward_push.rs:25-50). */
+typedef struct sb200_push_config {
+    double alpha;               /* 0.15 restart probability */
+    double epsilon;             /* 1e-6: a node is pushed while residual >= epsilon * max(degree, 1) */
+    uint64_t max_pushes;        /* 1 000 000; checked between rounds here (the last round may overshoot) */
+    double queue_threshold;     /* 1e-8: admission test residual / max(degree, 1) >= threshold, applied when not adaptive */
+    int32_t adaptive_threshold; /* 1: the reference decays the threshold while its queue is short; modelled as 0 */
+    int32_t reserved;
+} sb200_push_config;
+/* ForwardPushResult / BackwardPushResult (forward_push.rs:10-22) minus the two vectors (caller buffers). */
+typedef struct sb200_push_stats {
+    uint64_t push_count;
+    uint64_t nodes_visited;
+    double residual_norm;       /* L2 norm of the residual vector (forward_push.rs:217-219) */
+    /* extensions */
+    uint64_t rounds;            /* frontier-synchronous rounds (every node above its threshold is pushed at once) */
+    uint64_t kernel_launches;
+    double device_time_ms;
+} sb200_push_stats;
+void sb200_push_config_default(sb200_push_config *c);
+/* PushGraph::from_matrix(&CompressedSparseRow) (adjacency.rs:211-224): row u = out-edges of u, weights >= 0. */
+int32_t sb200_push_graph_from_csr(const uint64_t *row_ptr, const uint32_t *col_indices, const double *weights, uint64_t n,
+                                  sb200_push_graph **out);
+/* PushGraph::from_edges(num_nodes, &[(from, to, weight)]) (adjacency.rs:227-239): out-of-range edges are dropped. */
+int32_t sb200_push_graph_from_edges(uint64_t n, const uint64_t *from, const uint64_t *to, const double *weights,
+                                    uint64_t nedges, sb200_push_graph **out);
+int32_t sb200_push_graph_info(const sb200_push_graph *g, uint64_t *num_nodes, uint64_t *num_edges);
+int32_t sb200_push_graph_degrees(const sb200_push_graph *g, uint64_t node, double *out_degree, double *in_degree);
+void sb200_push_graph_free(sb200_push_graph *g);
+/* ForwardPushSolver::solve_single_source (nsources = 1: unit mass; an out-of-range source gives the all-zero result) /
+ * solve_multi_source (mass 1/nsources per listed source) (forward_push.rs:66-177). estimate / residual: n doubles each.
+ * The reference pushes one node at a time in priority order (its queue item has no Ord impl: the order is undefined);
+ * here every node above its threshold is pushed in the same round (deterministic, no atomics). Same push rule, same
+ * stopping condition, same invariants: estimate, residual >= 0, sum(estimate) + sum(residual) = 1 for the forward
+ * direction, residual < epsilon * max(degree, 1) everywhere at exit. */
+int32_t sb200_forward_push(const sb200_push_graph *g, const sb200_push_config *cfg, const uint64_t *sources,
+                           uint64_t nsources, double *estimate, double *residual, sb200_push_stats *stats);
+/* BackwardPushSolver::solve_single_target / solve_multi_target (backward_push.rs:66-220): mass moves to the
+ * predecessors with weight / max(out_degree(predecessor), 1); thresholds use the in-degree. */
+int32_t sb200_backward_push(const sb200_push_graph *g, const sb200_push_config *cfg, const uint64_t *targets,
+                            uint64_t ntargets, double *estimate, double *residual, sb200_push_stats *stats);
+
+/* ---------------------------------------------------------------------------------------------- */
 /* single-entry estimation and PageRank (TS-only front doors)               */
 /* ---------------------------------------------------------------------------------------------- */
 /* Batched estimate of x[rows[q]] for A x = b by absorbing random walks (Ulam-von Neumann estimator,

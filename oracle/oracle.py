@@ -53,6 +53,15 @@ class _Result(C.Structure):
                 ("last_term_norm", C.c_double), ("total_time_ms", C.c_double)]
 
 
+class _PushConfig(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("epsilon", C.c_double), ("max_pushes", C.c_uint64),
+                ("queue_threshold", C.c_double), ("adaptive_threshold", C.c_int)]
+
+
+class _PushStats(C.Structure):
+    _fields_ = [("push_count", C.c_uint64), ("nodes_visited", C.c_uint64), ("residual_norm", C.c_double)]
+
+
 class _CgResult(C.Structure):
     _fields_ = [("solution", C.POINTER(C.c_double)), ("residual_norm", C.c_double), ("iterations", C.c_uint64),
                 ("converged", C.c_int), ("matvec_count", C.c_uint64), ("total_flops", C.c_uint64)]
@@ -119,6 +128,10 @@ def lib(fast: bool = False, out_dir: str | None = None):
     L.orc_state_info.restype = None
     L.orc_state_free.argtypes = [C.c_void_p]
     L.orc_state_free.restype = None
+    L.orc_push_config_default.argtypes = [C.POINTER(_PushConfig)]
+    L.orc_push_config_default.restype = None
+    for f in (L.orc_forward_push, L.orc_backward_push):
+        f.argtypes = [C.POINTER(_Csr), C.POINTER(_PushConfig), u64p, C.c_uint64, f64p, f64p, C.POINTER(_PushStats)]
     L.orc_cg_solve.argtypes = [C.POINTER(_Csr), f64p, C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_int,
                                C.POINTER(_CgResult)]
     L.orc_gen_bench_k.argtypes = [C.c_uint64, C.c_double]
@@ -336,6 +349,49 @@ class NeumannState:
         return {"residual_norm": rn.value, "matvec_count": mv.value, "terms_computed": tc.value,
                 "series_converged": bool(sc.value), "last_term_norm": tn.value,
                 "error_upper_bound": bd.value if hb.value else None}
+
+
+@dataclass
+class PushResult:
+    """ForwardPushResult / BackwardPushResult (src/solver/forward_push.rs:10-22, backward_push.rs:10-22)"""
+    estimate: np.ndarray
+    residual: np.ndarray
+    push_count: int
+    nodes_visited: int
+    residual_norm: float
+
+    def extrapolated_solution(self, alpha):
+        """ForwardPushSolver::extrapolated_solution (forward_push.rs:317-327)"""
+        return self.estimate + alpha * self.residual
+
+
+def _push(fn_name, adj: Csr, seeds, alpha, epsilon, max_pushes, queue_threshold, adaptive_threshold):
+    L = lib()
+    c = _PushConfig()
+    L.orc_push_config_default(C.byref(c))
+    c.alpha, c.epsilon, c.max_pushes = alpha, epsilon, max_pushes
+    c.queue_threshold, c.adaptive_threshold = queue_threshold, int(adaptive_threshold)
+    s = _u64(np.atleast_1d(seeds))
+    est, res = np.zeros(adj.nrows), np.zeros(adj.nrows)
+    st = _PushStats()
+    a = adj.c()
+    rc = getattr(L, fn_name)(C.byref(a), C.byref(c), _p(s, C.c_uint64), len(s), _p(est, C.c_double), _p(res, C.c_double),
+                             C.byref(st))
+    if rc != OK:
+        raise OracleError(rc, fn_name)
+    return PushResult(est, res, int(st.push_count), int(st.nodes_visited), st.residual_norm)
+
+
+def forward_push(adj: Csr, sources, alpha=0.15, epsilon=1e-6, max_pushes=1_000_000, queue_threshold=1e-8,
+                 adaptive_threshold=True) -> PushResult:
+    """ForwardPushSolver::solve_single_source / solve_multi_source (src/solver/forward_push.rs:66-177) restated."""
+    return _push("orc_forward_push", adj, sources, alpha, epsilon, max_pushes, queue_threshold, adaptive_threshold)
+
+
+def backward_push(adj: Csr, targets, alpha=0.15, epsilon=1e-6, max_pushes=1_000_000, queue_threshold=1e-8,
+                  adaptive_threshold=True) -> PushResult:
+    """BackwardPushSolver::solve_single_target / solve_multi_target (src/solver/backward_push.rs:66-177) restated."""
+    return _push("orc_backward_push", adj, targets, alpha, epsilon, max_pushes, queue_threshold, adaptive_threshold)
 
 
 @dataclass

@@ -607,6 +607,175 @@ double orc_push_iterations(const orc_csr *m, const double *b, uint64_t nterms, i
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* forward / backward push (src/solver/forward_push.rs, src/solver/backward_push.rs)           */
+/* ------------------------------------------------------------------------------------------ */
+void orc_push_config_default(orc_push_config *c) { /* forward_push.rs:40-50 = backward_push.rs:40-50 */
+    c->alpha = 0.15;
+    c->epsilon = 1e-6;
+    c->max_pushes = 1000000;
+    c->queue_threshold = 1e-8;
+    c->adaptive_threshold = 1;
+}
+
+/* WorkQueue (src/graph/mod.rs:130-212): binary max-heap of (priority, node) + in_queue bit set + threshold */
+typedef struct { double pr; uint64_t node; } witem;
+typedef struct {
+    witem *heap;
+    uint64_t len, cap;
+    uint8_t *in_queue;
+    double threshold;
+} wqueue;
+
+static int witem_less(const witem *a, const witem *b) { /* derive(PartialOrd): priority, then node_id */
+    if (a->pr != b->pr) return a->pr < b->pr;
+    return a->node < b->node;
+}
+
+static void wq_push_if_threshold(wqueue *q, uint64_t node, double residual, double degree) { /* :171-181 */
+    double priority = degree > 0.0 ? residual / degree : residual;
+    if (!(priority >= q->threshold) || q->in_queue[node]) return;
+    if (q->len == q->cap) {
+        q->cap = q->cap ? q->cap * 2 : 64;
+        q->heap = (witem *)realloc(q->heap, q->cap * sizeof(witem));
+    }
+    uint64_t i = q->len++;
+    witem it = {priority, node};
+    while (i > 0) { /* sift up */
+        uint64_t parent = (i - 1) / 2;
+        if (!witem_less(&q->heap[parent], &it)) break;
+        q->heap[i] = q->heap[parent];
+        i = parent;
+    }
+    q->heap[i] = it;
+    q->in_queue[node] = 1;
+}
+
+static int wq_pop(wqueue *q, uint64_t *node) { /* :184-191 */
+    if (q->len == 0) return 0;
+    witem top = q->heap[0];
+    witem last = q->heap[--q->len];
+    uint64_t i = 0;
+    for (;;) { /* sift down */
+        uint64_t l = 2 * i + 1, r = l + 1, big = i;
+        const witem *cur = &last;
+        if (l < q->len && witem_less(cur, &q->heap[l])) { big = l; cur = &q->heap[l]; }
+        if (r < q->len && witem_less(cur, &q->heap[r])) { big = r; }
+        if (big == i) break;
+        q->heap[i] = q->heap[big];
+        i = big;
+    }
+    if (q->len) q->heap[i] = last;
+    q->in_queue[top.node] = 0;
+    *node = top.node;
+    return 1;
+}
+
+static void wq_adaptive(wqueue *q, uint64_t max_size, uint64_t min_size) { /* :204-212 */
+    if (q->len > max_size) q->threshold *= 1.1;
+    else if (q->len < min_size && q->threshold > 1e-12) q->threshold *= 0.9;
+}
+
+/* direction 0: forward (mass moves along out-edges, thresholds on the out-degree);
+ * direction 1: backward (mass moves to predecessors with weight / max(out_degree(pred), 1), thresholds on the in-degree) */
+static int push_run(const orc_csr *adj, const orc_push_config *cfg, const uint64_t *seeds, uint64_t nseeds,
+                    int direction, double *est, double *res, orc_push_stats *stats) {
+    if (adj->nrows != adj->ncols) return ORC_ERR_INVALID_INPUT;
+    uint64_t n = adj->nrows;
+    double *deg = (double *)calloc(n ? n : 1, sizeof(double));   /* row sums (adjacency.rs:214) */
+    double *rdeg = (double *)calloc(n ? n : 1, sizeof(double));  /* column sums (adjacency.rs:215) */
+    uint8_t *visited = (uint8_t *)calloc(n ? n : 1, 1);
+    wqueue q = {NULL, 0, 0, (uint8_t *)calloc(n ? n : 1, 1), cfg->queue_threshold};
+    /* transpose for the backward direction (mod.rs:93-127) */
+    uint32_t *tptr = NULL, *tcol = NULL;
+    double *tval = NULL;
+    for (uint64_t u = 0; u < n; u++)
+        for (uint64_t k = adj->row_ptr[u]; k < adj->row_ptr[u + 1]; k++) {
+            deg[u] += adj->values[k];
+            rdeg[adj->col_indices[k]] += adj->values[k];
+        }
+    if (direction == 1) {
+        tptr = (uint32_t *)calloc(n + 1, sizeof(uint32_t));
+        tcol = (uint32_t *)malloc((adj->nnz ? adj->nnz : 1) * sizeof(uint32_t));
+        tval = (double *)malloc((adj->nnz ? adj->nnz : 1) * sizeof(double));
+        for (uint64_t k = 0; k < adj->nnz; k++) tptr[adj->col_indices[k] + 1]++;
+        for (uint64_t i = 0; i < n; i++) tptr[i + 1] += tptr[i];
+        uint32_t *pos = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t));
+        memcpy(pos, tptr, n * sizeof(uint32_t));
+        for (uint64_t u = 0; u < n; u++)
+            for (uint64_t k = adj->row_ptr[u]; k < adj->row_ptr[u + 1]; k++) {
+                uint32_t c = adj->col_indices[k];
+                tcol[pos[c]] = (uint32_t)u;
+                tval[pos[c]] = adj->values[k];
+                pos[c]++;
+            }
+        free(pos);
+    }
+    const double *tdeg = direction ? rdeg : deg; /* the degree the thresholds use */
+    for (uint64_t i = 0; i < n; i++) est[i] = res[i] = 0.0;
+    uint64_t push_count = 0, nvisited = 0;
+    int any = 0;
+    if (nseeds == 1) { /* solve_single_source / solve_single_target: unit mass, out of range -> zero result */
+        if (seeds[0] < n) { res[seeds[0]] = 1.0; any = 1; }
+    } else if (nseeds > 1) { /* solve_multi_*: 1/len mass per listed seed, out-of-range ones are skipped */
+        double mass = 1.0 / (double)nseeds;
+        for (uint64_t s = 0; s < nseeds; s++) if (seeds[s] < n) { res[seeds[s]] += mass; any = 1; }
+    }
+    if (any)
+        for (uint64_t s = 0; s < nseeds; s++)
+            if (seeds[s] < n) wq_push_if_threshold(&q, seeds[s], res[seeds[s]], fmax(tdeg[seeds[s]], 1.0));
+    uint64_t node;
+    while (q.len > 0 && push_count < cfg->max_pushes) {
+        if (!wq_pop(&q, &node)) break;
+        if (res[node] < cfg->epsilon * fmax(tdeg[node], 1.0)) continue;
+        /* push_node / backward_push_node */
+        if (res[node] > 0.0) {
+            est[node] += cfg->alpha * res[node];
+            double remaining = (1.0 - cfg->alpha) * res[node];
+            res[node] = 0.0;
+            if (tdeg[node] > 0.0) {
+                if (direction == 0) {
+                    for (uint64_t k = adj->row_ptr[node]; k < adj->row_ptr[node + 1]; k++) {
+                        uint64_t v = adj->col_indices[k];
+                        res[v] += remaining * adj->values[k] / deg[node];
+                        wq_push_if_threshold(&q, v, res[v], fmax(deg[v], 1.0));
+                    }
+                } else {
+                    for (uint64_t k = tptr[node]; k < tptr[node + 1]; k++) {
+                        uint64_t p = tcol[k];
+                        double transition = tval[k] / fmax(deg[p], 1.0);
+                        res[p] += remaining * transition;
+                        wq_push_if_threshold(&q, p, res[p], fmax(rdeg[p], 1.0));
+                    }
+                }
+            } else { /* no edges in the push direction: the mass stays on the node */
+                res[node] += remaining;
+                wq_push_if_threshold(&q, node, res[node], 1.0);
+            }
+        }
+        if (!visited[node]) { visited[node] = 1; nvisited++; }
+        push_count++;
+        if (cfg->adaptive_threshold && push_count % 1000 == 0) wq_adaptive(&q, 10000, 100);
+    }
+    double nrm = 0.0;
+    for (uint64_t i = 0; i < n; i++) nrm += res[i] * res[i];
+    stats->push_count = push_count;
+    stats->nodes_visited = nvisited;
+    stats->residual_norm = any ? sqrt(nrm) : 0.0;
+    free(deg); free(rdeg); free(visited); free(q.heap); free(q.in_queue); free(tptr); free(tcol); free(tval);
+    return ORC_OK;
+}
+
+int orc_forward_push(const orc_csr *adj, const orc_push_config *cfg, const uint64_t *sources, uint64_t nsources,
+                     double *est, double *res, orc_push_stats *stats) {
+    return push_run(adj, cfg, sources, nsources, 0, est, res, stats);
+}
+
+int orc_backward_push(const orc_csr *adj, const orc_push_config *cfg, const uint64_t *targets, uint64_t ntargets,
+                      double *est, double *res, orc_push_stats *stats) {
+    return push_run(adj, cfg, targets, ntargets, 1, est, res, stats);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Conjugate gradient (src/optimized_solver.rs:182-295; fast_solver.rs:126-178; ultra_fast.rs:116-158) */
 /* ------------------------------------------------------------------------------------------ */
 static double cg_dot(const double *x, const double *y, uint64_t n, int variant) {

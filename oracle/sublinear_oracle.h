@@ -153,6 +153,32 @@ void orc_state_free(orc_state *st);
 double orc_push_iterations(const orc_csr *m, const double *b, uint64_t nterms, int spmv_variant,
                            int nthreads, double *x_out, double *t_out, double *term_norms);
 
+/* ---- forward / backward push: ForwardPushSolver::{solve_single_source, solve_multi_source}
+ * (src/solver/forward_push.rs:66-216) and BackwardPushSolver::{solve_single_target, solve_multi_target}
+ * (src/solver/backward_push.rs:66-220) over PushGraph::from_matrix (src/graph/adjacency.rs:211-224) with the
+ * WorkQueue / VisitedTracker of src/graph/mod.rs:130-260.
+ * `adj` is the adjacency CSR (row u = out-edges of u with weights); degrees are row sums, reverse degrees column sums.
+ * Pop order: WorkItem only derives PartialOrd (src/graph/mod.rs:141-147) and has no Ord impl, so BinaryHeap<WorkItem>
+ * does not compile in the reference; the restatement orders items by (priority, node_id), what the derive would give.
+ * Parity for this path is pinned by the properties the reference's own tests assert (mass, positivity, counts > 0),
+ * not by its pop order. est / res: n doubles each. */
+typedef struct {
+    double alpha;            /* 0.15 */
+    double epsilon;          /* 1e-6 */
+    uint64_t max_pushes;     /* 1 000 000 */
+    double queue_threshold;  /* 1e-8 */
+    int adaptive_threshold;  /* 1 */
+} orc_push_config;
+void orc_push_config_default(orc_push_config *c);
+typedef struct {
+    uint64_t push_count, nodes_visited;
+    double residual_norm;
+} orc_push_stats;
+int orc_forward_push(const orc_csr *adj, const orc_push_config *cfg, const uint64_t *sources, uint64_t nsources,
+                     double *est, double *res, orc_push_stats *stats);
+int orc_backward_push(const orc_csr *adj, const orc_push_config *cfg, const uint64_t *targets, uint64_t ntargets,
+                      double *est, double *res, orc_push_stats *stats);
+
 /* ---- conjugate gradient on the same SpMV ----
  * OptimizedConjugateGradientSolver::solve (src/optimized_solver.rs:182-295); the same loop is
  * FastConjugateGradient::solve (src/fast_solver.rs:126-178) and UltraFastCG::solve

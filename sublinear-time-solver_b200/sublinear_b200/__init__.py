@@ -68,6 +68,16 @@ class _Partial(C.Structure):
 _STREAM_CB = C.CFUNCTYPE(C.c_int32, C.POINTER(_Partial), C.c_void_p)
 
 
+class _PushConfig(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("epsilon", C.c_double), ("max_pushes", C.c_uint64),
+                ("queue_threshold", C.c_double), ("adaptive_threshold", C.c_int32), ("reserved", C.c_int32)]
+
+
+class _PushStats(C.Structure):
+    _fields_ = [("push_count", C.c_uint64), ("nodes_visited", C.c_uint64), ("residual_norm", C.c_double),
+                ("rounds", C.c_uint64), ("kernel_launches", C.c_uint64), ("device_time_ms", C.c_double)]
+
+
 class _CgConfig(C.Structure):
     _fields_ = [("max_iterations", C.c_uint64), ("tolerance", C.c_double), ("enable_profiling", C.c_int32),
                 ("reserved", C.c_int32)]
@@ -172,6 +182,14 @@ def lib():
         "sb200_state_info": ([vp, P(_StateInfo)], i32),
         "sb200_state_free": ([vp], None),
         "sb200_solve_streaming": ([vp, vp, vp, u64, P(_Options), _STREAM_CB, vp, P(_Result)], i32),
+        "sb200_push_config_default": ([P(_PushConfig)], None),
+        "sb200_push_graph_from_csr": ([vp, vp, vp, u64, P(vp)], i32),
+        "sb200_push_graph_from_edges": ([u64, vp, vp, vp, u64, P(vp)], i32),
+        "sb200_push_graph_info": ([vp, P(u64), P(u64)], i32),
+        "sb200_push_graph_degrees": ([vp, u64, P(f64), P(f64)], i32),
+        "sb200_push_graph_free": ([vp], None),
+        "sb200_forward_push": ([vp, P(_PushConfig), vp, u64, vp, vp, P(_PushStats)], i32),
+        "sb200_backward_push": ([vp, P(_PushConfig), vp, u64, vp, vp, P(_PushStats)], i32),
         "sb200_cg_config_default": ([P(_CgConfig)], None),
         "sb200_cg_solve": ([vp, vp, u64, P(_CgConfig), P(_CgResult)], i32),
         "sb200_cg_solve_into": ([vp, vp, u64, P(_CgConfig), vp, P(_CgResult)], i32),
@@ -730,6 +748,136 @@ class NeumannState:
 
     def reset(self):
         _check(lib().sb200_state_reset(self._h))
+
+
+@dataclass
+class PushConfig:
+    """`ForwardPushConfig` / `BackwardPushConfig` (src/solver/forward_push.rs:25-50, backward_push.rs:25-50)."""
+    alpha: float = 0.15
+    epsilon: float = 1e-6
+    max_pushes: int = 1_000_000
+    queue_threshold: float = 1e-8
+    adaptive_threshold: bool = True
+
+    def _c(self):
+        c = _PushConfig()
+        lib().sb200_push_config_default(C.byref(c))
+        c.alpha, c.epsilon, c.max_pushes = self.alpha, self.epsilon, self.max_pushes
+        c.queue_threshold, c.adaptive_threshold = self.queue_threshold, int(self.adaptive_threshold)
+        return c
+
+
+@dataclass
+class PushResult:
+    """`ForwardPushResult` / `BackwardPushResult` (src/solver/forward_push.rs:10-22) + extension fields."""
+    estimate: np.ndarray
+    residual: np.ndarray
+    push_count: int
+    nodes_visited: int
+    residual_norm: float
+    rounds: int
+    kernel_launches: int
+    device_time_ms: float
+
+
+class PushGraph:
+    """`PushGraph` (src/graph/adjacency.rs:199-277), resident in HBM."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.sb200_push_graph_free(self._h)
+            self._h = None
+
+    @staticmethod
+    def from_matrix(row_ptr, col_indices, values, n) -> "PushGraph":
+        """`PushGraph::from_matrix(&CompressedSparseRow)`: row u holds the out-edges of u."""
+        rp, ci, v = _u64(row_ptr), np.ascontiguousarray(col_indices, dtype=np.uint32), _f64(values)
+        h = C.c_void_p()
+        _check(lib().sb200_push_graph_from_csr(_ptr(rp), _ptr(ci), _ptr(v), n, C.byref(h)))
+        return PushGraph(h)
+
+    @staticmethod
+    def from_edges(num_nodes, edges) -> "PushGraph":
+        """`PushGraph::from_edges(num_nodes, &[(from, to, weight)])`"""
+        f = _u64([e[0] for e in edges])
+        t = _u64([e[1] for e in edges])
+        w = _f64([e[2] for e in edges])
+        h = C.c_void_p()
+        _check(lib().sb200_push_graph_from_edges(num_nodes, _ptr(f), _ptr(t), _ptr(w), len(w), C.byref(h)))
+        return PushGraph(h)
+
+    def num_nodes(self):
+        n = C.c_uint64()
+        _check(lib().sb200_push_graph_info(self._h, C.byref(n), None))
+        return n.value
+
+    def num_edges(self):
+        e = C.c_uint64()
+        _check(lib().sb200_push_graph_info(self._h, None, C.byref(e)))
+        return e.value
+
+    def out_degree(self, node):
+        d = C.c_double()
+        _check(lib().sb200_push_graph_degrees(self._h, node, C.byref(d), None))
+        return d.value
+
+    def in_degree(self, node):
+        d = C.c_double()
+        _check(lib().sb200_push_graph_degrees(self._h, node, None, C.byref(d)))
+        return d.value
+
+
+class _PushSolver:
+    _fn = None
+
+    def __init__(self, graph: PushGraph, config: PushConfig | None = None):
+        self.graph, self.config = graph, config or PushConfig()
+
+    def _run(self, seeds) -> PushResult:
+        s = _u64(np.atleast_1d(seeds))
+        n = self.graph.num_nodes()
+        est, res = np.zeros(n), np.zeros(n)
+        c = self.config._c()
+        st = _PushStats()
+        _check(getattr(lib(), self._fn)(self.graph._h, C.byref(c), _ptr(s), len(s), _ptr(est), _ptr(res), C.byref(st)))
+        return PushResult(est, res, int(st.push_count), int(st.nodes_visited), st.residual_norm, int(st.rounds),
+                          int(st.kernel_launches), st.device_time_ms)
+
+
+class ForwardPushSolver(_PushSolver):
+    """`ForwardPushSolver` (src/solver/forward_push.rs:52-328) as frontier-synchronous rounds on the device."""
+    _fn = "sb200_forward_push"
+
+    def solve_single_source(self, source) -> PushResult:
+        return self._run([source])
+
+    def solve_multi_source(self, sources) -> PushResult:
+        return self._run(list(sources))
+
+    def query_single_entry(self, source, target) -> float:
+        r = self.solve_single_source(source)
+        return float(r.estimate[target]) if target < len(r.estimate) else 0.0
+
+    def extrapolated_solution(self, result: PushResult) -> np.ndarray:
+        return result.estimate + self.config.alpha * result.residual
+
+
+class BackwardPushSolver(_PushSolver):
+    """`BackwardPushSolver` (src/solver/backward_push.rs:52-330)."""
+    _fn = "sb200_backward_push"
+
+    def solve_single_target(self, target) -> PushResult:
+        return self._run([target])
+
+    def solve_multi_target(self, targets) -> PushResult:
+        return self._run(list(targets))
+
+    def query_transition_probability(self, source, target) -> float:
+        r = self.solve_single_target(target)
+        return float(r.estimate[source]) if source < len(r.estimate) else 0.0
 
 
 def push_iterations_dev(matrix: SparseMatrix, b_ptr: int, n: int, nterms: int, x_ptr: int = 0, t_ptr: int = 0,
