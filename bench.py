@@ -208,6 +208,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout must carry ONE JSON line, but NCCL prints its version banner (NCCL_DEBUG=VERSION) with a C-level write to
+    # fd 1: keep a private handle on the real stdout for the result and point fd 1 at stderr for everything else
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     if args.warmup < 3:
         args.warmup = 3
     if not torch.cuda.is_available():
@@ -217,8 +222,6 @@ def main():
     dist = world > 1
     if dist:
         import torch.distributed as td
-        # stdout carries ONE JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     size, sparsity = WORKLOADS[args.workload]
@@ -411,7 +414,8 @@ def main():
                     "api": "sb200_solve_into (host b -> host x)" if not dist else "sb200_dist_solve (host b_local -> host x_local)"},
             "gpu_launches": launches, "clocks": clocks,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
     if dist:
         td.destroy_process_group()
 
