@@ -7,6 +7,10 @@
 //   sublinear::SolverError    <-> SolverError   (src/error.rs:16-138), thrown where Rust returns Err(..)
 //   sublinear::OptimizedSparseMatrix / OptimizedConjugateGradientSolver / OptimizedSolverConfig / OptimizedSolverResult
 //                             <-> src/optimized_solver.rs:16-340 (the CG consumer of the same SpMV kernel)
+//   sublinear::NeumannState + NeumannSolver::{initialize, step, is_converged, extract_solution, update_rhs}
+//                             <-> trait SolverAlgorithm / SolverState (src/solver/mod.rs:223-352, neumann.rs:350-462)
+//   sublinear::PushGraph / ForwardPushSolver / BackwardPushSolver
+//                             <-> src/graph/adjacency.rs:199-277, src/solver/forward_push.rs, backward_push.rs
 // Header only; link against libsublinear_b200.so. The Rust toolchain is not available in the build image, so this is
 // the compiled-language host layer (the Rust shim in ../rust/ is the same mapping, shipped unbuilt).
 #pragma once
@@ -185,6 +189,8 @@ private:
     sb200_matrix *h_ = nullptr;
 };
 
+enum class StepResult { Continue, Converged };  // src/solver/mod.rs:355-363 (Failed(String) surfaces as SolverError)
+
 class NeumannSolver {
 public:
     NeumannSolver(size_t max_terms, Precision series_tolerance) { detail::check(sb200_neumann_new(max_terms, series_tolerance, &h_)); }
@@ -218,10 +224,77 @@ public:
         return out;
     }
 
+    // ---- trait SolverAlgorithm, the stepping half (src/solver/mod.rs:223-252) ----
+    // initialize(&self, matrix, b, options) -> Result<State>
+    inline class NeumannState initialize(const SparseMatrix &matrix, const std::vector<Precision> &b,
+                                         const SolverOptions &options = {}) const;
+    // step(&self, &mut state) -> Result<StepResult>: the body the reference left commented out (neumann.rs:404-418)
+    inline StepResult step(class NeumannState &state) const;
+    inline bool is_converged(const class NeumannState &state) const;
+    inline std::vector<Precision> extract_solution(const class NeumannState &state) const;
+    inline void update_rhs(class NeumannState &state, const std::vector<std::pair<size_t, Precision>> &delta_b) const;
+
 private:
     explicit NeumannSolver(sb200_solver *h) : h_(h) {}
     sb200_solver *h_ = nullptr;
 };
+
+// NeumannState behind trait SolverState (src/solver/mod.rs:336-352, neumann.rs:350-378). It shares ownership of the
+// matrix handle, so it may outlive the SparseMatrix it was initialised from.
+class NeumannState {
+public:
+    NeumannState(NeumannState &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    NeumannState(const NeumannState &) = delete;
+    ~NeumannState() { sb200_state_free(h_); }
+    Precision residual_norm() const { return info().residual_norm; }
+    size_t matvec_count() const { return info().matvec_count; }
+    std::optional<Precision> error_bounds() const {
+        const auto i = info();
+        return i.has_error_bounds ? std::optional<Precision>(i.error_upper_bound) : std::nullopt;
+    }
+    size_t memory_usage() const { return info().memory_bytes; }
+    size_t terms_computed() const { return info().terms_computed; }
+    bool series_converged() const { return info().series_converged != 0; }
+    void reset() { detail::check(sb200_state_reset(h_)); }
+    sb200_state *handle() const { return h_; }
+
+private:
+    friend class NeumannSolver;
+    explicit NeumannState(sb200_state *h) : h_(h) {}
+    sb200_state_info_t info() const { sb200_state_info_t i; detail::check(sb200_state_info(h_, &i)); return i; }
+    sb200_state *h_ = nullptr;
+};
+
+inline NeumannState NeumannSolver::initialize(const SparseMatrix &matrix, const std::vector<Precision> &b,
+                                              const SolverOptions &options) const {
+    sb200_options o = options.to_c();
+    sb200_state *st = nullptr;
+    detail::check(sb200_neumann_initialize(h_, matrix.handle(), b.data(), b.size(), &o, &st));
+    return NeumannState(st);
+}
+inline StepResult NeumannSolver::step(NeumannState &state) const {
+    int32_t r = 0;
+    detail::check(sb200_state_step(state.handle(), &r));
+    return r == SB200_STEP_CONVERGED ? StepResult::Converged : StepResult::Continue;
+}
+inline bool NeumannSolver::is_converged(const NeumannState &state) const {
+    int32_t c = 0;
+    detail::check(sb200_state_is_converged(state.handle(), &c));
+    return c != 0;
+}
+inline std::vector<Precision> NeumannSolver::extract_solution(const NeumannState &state) const {
+    sb200_state_info_t i;
+    detail::check(sb200_state_info(state.handle(), &i));
+    std::vector<Precision> x(i.dimension);
+    detail::check(sb200_state_extract_solution(state.handle(), x.data(), x.size()));
+    return x;
+}
+inline void NeumannSolver::update_rhs(NeumannState &state, const std::vector<std::pair<size_t, Precision>> &delta_b) const {
+    std::vector<uint64_t> idx(delta_b.size());
+    std::vector<double> dl(delta_b.size());
+    for (size_t k = 0; k < delta_b.size(); k++) { idx[k] = delta_b[k].first; dl[k] = delta_b[k].second; }
+    detail::check(sb200_state_update_rhs(state.handle(), idx.data(), dl.data(), dl.size()));
+}
 
 // ---- conjugate gradient on the same SpMV kernel (src/optimized_solver.rs) ---------------------------------------
 
@@ -301,6 +374,110 @@ public:
 private:
     OptimizedSolverConfig config_;
     OptimizedSolverStats stats_;
+};
+
+// ---- forward / backward push (src/graph/adjacency.rs, src/solver/forward_push.rs, backward_push.rs) ---------------
+
+class PushGraph {
+public:
+    // PushGraph::from_matrix(&CompressedSparseRow) (adjacency.rs:211-224)
+    static PushGraph from_matrix(const std::vector<uint64_t> &row_ptr, const std::vector<uint32_t> &col_indices,
+                                 const std::vector<Precision> &values) {
+        sb200_push_graph *h = nullptr;
+        detail::check(sb200_push_graph_from_csr(row_ptr.data(), col_indices.data(), values.data(), row_ptr.size() - 1, &h));
+        return PushGraph(h);
+    }
+    // PushGraph::from_edges(num_nodes, &[(from, to, weight)]) (adjacency.rs:227-239)
+    static PushGraph from_edges(size_t num_nodes, const std::vector<std::tuple<size_t, size_t, Precision>> &edges) {
+        std::vector<uint64_t> f(edges.size()), t(edges.size());
+        std::vector<double> w(edges.size());
+        for (size_t i = 0; i < edges.size(); i++) { f[i] = std::get<0>(edges[i]); t[i] = std::get<1>(edges[i]); w[i] = std::get<2>(edges[i]); }
+        sb200_push_graph *h = nullptr;
+        detail::check(sb200_push_graph_from_edges(num_nodes, f.data(), t.data(), w.data(), w.size(), &h));
+        return PushGraph(h);
+    }
+    PushGraph(PushGraph &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    PushGraph(const PushGraph &) = delete;
+    ~PushGraph() { sb200_push_graph_free(h_); }
+    size_t num_nodes() const { uint64_t n; detail::check(sb200_push_graph_info(h_, &n, nullptr)); return n; }
+    size_t num_edges() const { uint64_t e; detail::check(sb200_push_graph_info(h_, nullptr, &e)); return e; }
+    Precision out_degree(size_t node) const { double d; detail::check(sb200_push_graph_degrees(h_, node, &d, nullptr)); return d; }
+    Precision in_degree(size_t node) const { double d; detail::check(sb200_push_graph_degrees(h_, node, nullptr, &d)); return d; }
+    const sb200_push_graph *handle() const { return h_; }
+
+private:
+    explicit PushGraph(sb200_push_graph *h) : h_(h) {}
+    sb200_push_graph *h_ = nullptr;
+};
+
+struct PushConfig {  // ForwardPushConfig / BackwardPushConfig (forward_push.rs:25-50)
+    Precision alpha = 0.15, epsilon = 1e-6;
+    size_t max_pushes = 1000000;
+    Precision queue_threshold = 1e-8;
+    bool adaptive_threshold = true;
+    sb200_push_config to_c() const {
+        sb200_push_config c;
+        sb200_push_config_default(&c);
+        c.alpha = alpha; c.epsilon = epsilon; c.max_pushes = max_pushes; c.queue_threshold = queue_threshold;
+        c.adaptive_threshold = adaptive_threshold;
+        return c;
+    }
+};
+
+struct PushResult {  // ForwardPushResult / BackwardPushResult (forward_push.rs:10-22)
+    std::vector<Precision> estimate, residual;
+    size_t push_count = 0, nodes_visited = 0;
+    Precision residual_norm = 0.0;
+};
+
+namespace detail {
+template <typename Fn>
+inline PushResult run_push(Fn fn, const PushGraph &g, const PushConfig &cfg, const std::vector<size_t> &seeds) {
+    const sb200_push_config c = cfg.to_c();
+    std::vector<uint64_t> s(seeds.begin(), seeds.end());
+    PushResult r;
+    r.estimate.assign(g.num_nodes(), 0.0);
+    r.residual.assign(g.num_nodes(), 0.0);
+    sb200_push_stats st;
+    check(fn(g.handle(), &c, s.data(), s.size(), r.estimate.data(), r.residual.data(), &st));
+    r.push_count = st.push_count; r.nodes_visited = st.nodes_visited; r.residual_norm = st.residual_norm;
+    return r;
+}
+}  // namespace detail
+
+class ForwardPushSolver {  // forward_push.rs:52-328
+public:
+    ForwardPushSolver(PushGraph graph, PushConfig config = {}) : graph_(std::move(graph)), config_(config) {}
+    PushResult solve_single_source(size_t source) const { return detail::run_push(sb200_forward_push, graph_, config_, {source}); }
+    PushResult solve_multi_source(const std::vector<size_t> &sources) const { return detail::run_push(sb200_forward_push, graph_, config_, sources); }
+    Precision query_single_entry(size_t source, size_t target) const {
+        const PushResult r = solve_single_source(source);
+        return target < r.estimate.size() ? r.estimate[target] : 0.0;
+    }
+    std::vector<Precision> extrapolated_solution(const PushResult &result) const {  // :317-327
+        std::vector<Precision> x = result.estimate;
+        for (size_t i = 0; i < x.size(); i++) x[i] += config_.alpha * result.residual[i];
+        return x;
+    }
+
+private:
+    PushGraph graph_;
+    PushConfig config_;
+};
+
+class BackwardPushSolver {  // backward_push.rs:52-330
+public:
+    BackwardPushSolver(PushGraph graph, PushConfig config = {}) : graph_(std::move(graph)), config_(config) {}
+    PushResult solve_single_target(size_t target) const { return detail::run_push(sb200_backward_push, graph_, config_, {target}); }
+    PushResult solve_multi_target(const std::vector<size_t> &targets) const { return detail::run_push(sb200_backward_push, graph_, config_, targets); }
+    Precision query_transition_probability(size_t source, size_t target) const {
+        const PushResult r = solve_single_target(target);
+        return source < r.estimate.size() ? r.estimate[source] : 0.0;
+    }
+
+private:
+    PushGraph graph_;
+    PushConfig config_;
 };
 
 }  // namespace sublinear

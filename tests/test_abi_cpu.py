@@ -145,6 +145,17 @@ def test_cpp_mirror_of_reference_api_compiles_and_links(tmp_path):
     _build_cpp_unit_tests(tmp_path)
 
 
+def test_cpp_mirror_covers_state_push_and_cg_api(tmp_path):
+    """every wrapper of cpp/sublinear.hpp (stepping interface, push solvers, CG) compiles against the header and links
+    against the library; nothing touches a device"""
+    exe = os.path.join(str(tmp_path), "compile_api_mirror")
+    src = os.path.join(os.path.dirname(__file__), "cpp", "compile_api_mirror.cpp")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O0", "-Wall", "-o", exe, src, "-L", sb.PKG_DIR, "-lsublinear_b200",
+                        f"-Wl,-rpath,{sb.PKG_DIR}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert subprocess.run([exe], capture_output=True).returncode == 0
+
+
 @pytest.mark.gpu
 def test_cpp_reference_unit_tests_run(tmp_path):
     exe = _build_cpp_unit_tests(tmp_path)
