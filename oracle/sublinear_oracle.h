@@ -160,8 +160,9 @@ double orc_push_iterations(const orc_csr *m, const double *b, uint64_t nterms, i
  * `adj` is the adjacency CSR (row u = out-edges of u with weights); degrees are row sums, reverse degrees column sums.
  * Pop order: WorkItem only derives PartialOrd (src/graph/mod.rs:141-147) and has no Ord impl, so BinaryHeap<WorkItem>
  * does not compile in the reference; the restatement orders items by (priority, node_id), what the derive would give.
- * Parity for this path is pinned by the properties the reference's own tests assert (mass, positivity, counts > 0),
- * not by its pop order. est / res: n doubles each. */
+ * PARITY UNPINNED for this path: the reference holds no golden vectors for it and its own source does not fix a pop
+ * order; the restatement is held to the properties the reference's tests assert (mass, positivity, counts > 0) and to
+ * the exact personalised PageRank (tests/test_push.py). est / res: n doubles each. */
 typedef struct {
     double alpha;            /* 0.15 */
     double epsilon;          /* 1e-6 */
