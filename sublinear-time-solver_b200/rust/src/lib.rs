@@ -12,6 +12,19 @@ use sublinear::types::{ErrorBoundMethod, ErrorBounds, MemoryInfo, Precision, Sol
 #[repr(C)] pub struct sb200_matrix { _p: [u8; 0] }
 #[repr(C)] pub struct sb200_solver { _p: [u8; 0] }
 #[repr(C)] pub struct sb200_state { _p: [u8; 0] }
+#[repr(C)] pub struct sb200_push_graph { _p: [u8; 0] }
+
+#[repr(C)]
+pub struct sb200_push_config {
+    pub alpha: f64, pub epsilon: f64, pub max_pushes: u64, pub queue_threshold: f64, pub adaptive_threshold: i32,
+    pub reserved: i32,
+}
+
+#[repr(C)]
+pub struct sb200_push_stats {
+    pub push_count: u64, pub nodes_visited: u64, pub residual_norm: f64, pub rounds: u64, pub kernel_launches: u64,
+    pub device_time_ms: f64,
+}
 
 #[repr(C)]
 pub struct sb200_state_info_t {
@@ -71,6 +84,16 @@ extern "C" {
     fn sb200_state_reset(st: *mut sb200_state) -> i32;
     fn sb200_state_info(st: *const sb200_state, info: *mut sb200_state_info_t) -> i32;
     fn sb200_state_free(st: *mut sb200_state);
+    // PushGraph / ForwardPushSolver / BackwardPushSolver (src/graph/adjacency.rs:199-277, src/solver/forward_push.rs,
+    // src/solver/backward_push.rs)
+    fn sb200_push_config_default(c: *mut sb200_push_config);
+    fn sb200_push_graph_from_csr(row_ptr: *const u64, col_indices: *const u32, weights: *const f64, n: u64,
+                                 out: *mut *mut sb200_push_graph) -> i32;
+    fn sb200_push_graph_free(g: *mut sb200_push_graph);
+    fn sb200_forward_push(g: *const sb200_push_graph, cfg: *const sb200_push_config, sources: *const u64, nsources: u64,
+                          estimate: *mut f64, residual: *mut f64, stats: *mut sb200_push_stats) -> i32;
+    fn sb200_backward_push(g: *const sb200_push_graph, cfg: *const sb200_push_config, targets: *const u64, ntargets: u64,
+                           estimate: *mut f64, residual: *mut f64, stats: *mut sb200_push_stats) -> i32;
     // OptimizedConjugateGradientSolver (src/optimized_solver.rs:168-295)
     fn sb200_cg_config_default(c: *mut sb200_cg_config);
     fn sb200_cg_solve_into(m: *const sb200_matrix, b: *const f64, blen: u64, cfg: *const sb200_cg_config,
@@ -246,3 +269,45 @@ pub fn b200_cg_solve(matrix: &B200Matrix, b: &[Precision], max_iterations: usize
     if rc != 0 { return Err(last_error()); }   // "Matrix must be square" / length mismatch (:188-193)
     Ok((x, r.residual_norm, r.iterations as usize, r.converged != 0))
 }
+
+/// `PushGraph` + `ForwardPushSolver::solve_single_source` / `BackwardPushSolver::solve_single_target` on the device
+/// (src/solver/forward_push.rs:66-121, src/solver/backward_push.rs:66-121). Returns the fields of
+/// `ForwardPushResult`: (estimate, residual, push_count, nodes_visited, residual_norm).
+pub struct B200PushGraph { h: *mut sb200_push_graph, n: usize }
+unsafe impl Send for B200PushGraph {}
+unsafe impl Sync for B200PushGraph {}
+
+impl B200PushGraph {
+    /// `PushGraph::from_matrix(&CompressedSparseRow)` (src/graph/adjacency.rs:211-224)
+    pub fn from_matrix(row_ptr: &[usize], col_indices: &[usize], values: &[f64]) -> Result<Self> {
+        let rp: Vec<u64> = row_ptr.iter().map(|&v| v as u64).collect();
+        let ci: Vec<u32> = col_indices.iter().map(|&v| v as u32).collect();
+        let mut h = std::ptr::null_mut();
+        let n = row_ptr.len() - 1;
+        let rc = unsafe { sb200_push_graph_from_csr(rp.as_ptr(), ci.as_ptr(), values.as_ptr(), n as u64, &mut h) };
+        if rc != 0 { return Err(to_error(rc, &unsafe { std::mem::zeroed() }, 0.0)); }
+        Ok(Self { h, n })
+    }
+    fn run(&self, backward: bool, alpha: f64, epsilon: f64, seed: usize) -> Result<(Vec<f64>, Vec<f64>, usize, usize, f64)> {
+        let mut c: sb200_push_config = unsafe { std::mem::zeroed() };
+        unsafe { sb200_push_config_default(&mut c) };
+        c.alpha = alpha;
+        c.epsilon = epsilon;
+        let (mut est, mut res) = (vec![0.0; self.n], vec![0.0; self.n]);
+        let mut st: sb200_push_stats = unsafe { std::mem::zeroed() };
+        let s = [seed as u64];
+        let rc = unsafe {
+            if backward { sb200_backward_push(self.h, &c, s.as_ptr(), 1, est.as_mut_ptr(), res.as_mut_ptr(), &mut st) }
+            else { sb200_forward_push(self.h, &c, s.as_ptr(), 1, est.as_mut_ptr(), res.as_mut_ptr(), &mut st) }
+        };
+        if rc != 0 { return Err(to_error(rc, &unsafe { std::mem::zeroed() }, 0.0)); }
+        Ok((est, res, st.push_count as usize, st.nodes_visited as usize, st.residual_norm))
+    }
+    pub fn forward_push_single_source(&self, alpha: f64, epsilon: f64, source: usize) -> Result<(Vec<f64>, Vec<f64>, usize, usize, f64)> {
+        self.run(false, alpha, epsilon, source)
+    }
+    pub fn backward_push_single_target(&self, alpha: f64, epsilon: f64, target: usize) -> Result<(Vec<f64>, Vec<f64>, usize, usize, f64)> {
+        self.run(true, alpha, epsilon, target)
+    }
+}
+impl Drop for B200PushGraph { fn drop(&mut self) { unsafe { sb200_push_graph_free(self.h) } } }
