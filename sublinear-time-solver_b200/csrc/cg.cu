@@ -9,7 +9,7 @@
 //   cg_vec phase 1       x += alpha p ; r -= alpha ap ; partial r.r ; last CTA: beta, rsold, iteration count, loop test
 //   cg_vec phase 2       p = r + beta p
 // The loop decisions (`iteration < max_iterations`, `rsold <= tolerance^2`, the p.ap guard) are taken on the device by
-// the last CTA of each reducing kernel (LoopCtl, kernels.cu); the host enqueues iterations in batches and reads the
+// the last CTA of each reducing kernel (LoopCtl, device_util.cuh); the host enqueues iterations in batches and reads the
 // 1-cache-line loop state back once per batch. Dot products are fixed-order two-stage reductions (CTA tree, then the
 // CTA partials in index order): reproducible run to run, different from the reference's sequential sums in the last
 // bits only (the reference's own three CG variants differ from each other in the same way).

@@ -191,7 +191,7 @@ struct TileKernelArgs {
     PeerExchange px;      // row-partitioned P2P exchange (warp-stream kernel only)
 };
 
-// launchers (kernels.cu). grid = 0 -> persistent grid sized from occupancy.
+// launchers (kernels.cu; ingest passes in kernels_ingest.cu, vector passes in kernels_vec.cu). grid = 0 -> persistent grid sized from occupancy.
 int32_t launch_tile_kernel(int cfg, Epilogue epi, const TileKernelArgs &a, cudaStream_t stream);
 int tile_kernel_max_grid(int cfg, Epilogue epi);
 // setup pass over the CSR (K4): per-row dominance, diagonal and its inverse
@@ -250,7 +250,7 @@ int32_t launch_dist_tail(LoopCtl *ctl, int kind, uint32_t it, int last_in_iter, 
 int32_t launch_peer_wait(LoopCtl *ctl, const unsigned long long *flags_local, const double *slots_local, int world,
                          unsigned long long epoch_base, int kind, uint32_t it, int last_in_iter, int identity_res,
                          int force, double *norm_log, cudaStream_t stream);
-// conjugate gradient vector passes (kernels.cu). phase 0: x = 0, r = p = b, rsold = b.b ; phase 1: x += alpha p,
+// conjugate gradient vector passes (kernels_vec.cu). phase 0: x = 0, r = p = b, rsold = b.b ; phase 1: x += alpha p,
 // r -= alpha ap, rsnew = r.r (then beta, rsold, iteration count and the loop decision in the tail) ; phase 2: p = r + beta p
 struct CgVecArgs {
     const double *b;   // phase 0

@@ -1,5 +1,5 @@
 // device_util.cuh — PTX helpers, deterministic reductions and the device-side loop control shared by the kernel
-// translation units (kernels.cu, kernels_tile.cu, kernels_vec.cu). Internal; nothing here is part of the ABI.
+// translation units (kernels.cu, kernels_tile.cu, kernels_vec.cu, kernels_ingest.cu). Internal; nothing here is part of the ABI.
 #pragma once
 
 #include "common.hpp"

@@ -2,7 +2,7 @@
 //
 // Host control flow of NeumannSolver::solve (ref src/solver/neumann.rs:469-555).  The per-iteration decisions
 // (series_converged, residual <= tolerance, NumericalInstability, max_iterations) are taken ON THE DEVICE by the
-// last CTA of each kernel (LoopCtl, kernels.cu); the host only enqueues iterations in batches and reads the
+// last CTA of each kernel (LoopCtl, device_util.cuh); the host only enqueues iterations in batches and reads the
 // loop state back once per batch, so a term costs one kernel launch and no host synchronisation.
 #include <chrono>
 #include <cmath>
