@@ -122,6 +122,23 @@ class CpuPath:
                                           self.O.SPMV_PARALLEL, self.cores, None, None, None)
         return self.nnz * iters / secs, secs
 
+    def solve(self, mode=0):
+        """one full NeumannSolver::default().solve (the step bench.py's GPU arm times) with the row-chunk parallel SpMV"""
+        import numpy as np
+        C, O = self.C, self.O
+        o = O._Options()
+        self.L.orc_options_default(C.byref(o))
+        o.mode, o.spmv_variant, o.nthreads = mode, O.SPMV_PARALLEL, self.cores
+        x = np.zeros(len(self.b))
+        r = O._Result()
+        r.solution = x.ctypes.data_as(C.POINTER(C.c_double))
+        t0 = time.perf_counter()
+        rc = self.L.orc_neumann_solve(C.byref(self.raw), self.b.ctypes.data_as(C.POINTER(C.c_double)), len(self.b),
+                                      C.byref(o), C.byref(r))
+        secs = time.perf_counter() - t0
+        assert rc == 0, rc
+        return int(r.matvec_count), int(r.terms_computed), secs
+
     def close(self):
         self.L.orc_csr_free(self.C.byref(self.raw))
 
@@ -142,23 +159,29 @@ def run_reference(args):
     size, sparsity = WORKLOADS[args.workload]
     s_size, s_sparsity = cpu_sample_shape(size, sparsity)
     cpu = CpuPath(s_size, s_sparsity)
-    sample = (f"gen_bench({s_size}, {s_sparsity:g}) nnz={cpu.nnz}, {args.cpu_iters} push iterations "
-              f"(SpMV + diagonal scale + term/solution update + norm) per step, OpenMP row chunks on {cpu.cores} threads")
+    # the same step as the GPU arm: one full default solve (term recurrence + residual every 5th iteration + final
+    # residual), counted in SpMV-equivalents; warm-up bounded to one solve (each is ~1.5 s of all-core CPU work)
+    mode = 0 if args.mode == "correct" else 1
     vals = []
-    for i in range(args.warmup + args.steps):
-        v, secs = cpu.run(args.cpu_iters)
-        if i >= args.warmup:
-            vals.append((v, secs))
+    mv = terms = 0
+    for i in range(min(args.warmup, 1) + args.steps):
+        mv, terms, secs = cpu.solve(mode)
+        if i >= min(args.warmup, 1):
+            vals.append(secs)
     cpu.close()
-    total_s = sum(s for _, s in vals)
-    value = cpu.nnz * args.cpu_iters * len(vals) / total_s
+    sample = (f"gen_bench({s_size}, {s_sparsity:g}) nnz={cpu.nnz}, one NeumannSolver::default().solve per step "
+              f"({terms} terms, {mv} SpMV-equivalents: SpMV + diagonal scale + term/solution update + norms), OpenMP row "
+              f"chunks on {cpu.cores} threads")
+    total_s = sum(vals)
+    value = cpu.nnz * mv * len(vals) / total_s
     ms = 1e3 * total_s / len(vals)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "n": s_size, "nnz": cpu.nnz,
                        "generator": "gen_bench(size, sparsity) = benches/performance_benchmarks.rs:12-43, uniform-random columns",
-                       "step": sample},
+                       "step": "one NeumannSolver::default().solve (50 terms / 1e-8, tolerance 1e-6, residual every 5th iteration)",
+                       "mode": args.mode, "terms_per_step": terms, "matvecs_per_step": mv, "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -195,6 +218,7 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=5)
     ap.add_argument("--cpu-baseline-iters", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed solution")
     ap.add_argument("--mode", default="correct", choices=["correct", "ref_compat"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -334,22 +358,24 @@ def main():
     roofline = None
     layout = m.storage_info()
     kernel_name = {sb.LAYOUT_SELL32: "sell_kernel<EPI_PUSH,256,8> (SELL-32 layout, no shared memory)",
-                   sb.LAYOUT_CSR_SLABS: "warp_kernel<EPI_PUSH,256,4>, one pass per column slab of the term vector "
-                                        "(the measured launch is the whole pass set)",
+                   sb.LAYOUT_CSR_SLABS: "slab_kernel<EPI_PUSH,256,3>: one fused launch walks the column slabs of the term "
+                                        "vector (CSR order kept, row sums carried from slab to slab)",
                    sb.LAYOUT_CSR: "warp_kernel<EPI_PUSH,256,4> (CSR slices)"}[layout["layout"]]
     if push_cnt:
         t_push = push_ms / push_cnt * 1e-3
         alg = algorithmic_bytes_push(n_local, nnz_local) + (8 * (size - n_local) if dist else 0)
         ach = alg / t_push / 1e9
-        traffic = None
+        # DRAM bytes per launch come from an ncu capture (profiles/scripts/r2_ncu_push.sh -> profiles/push_traffic.json);
+        # the entry is used only if it was captured on the kernel that ran here, else null
+        traffic, traffic_src = None, None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "push_traffic.json"))).get(args.workload)
-            if tr and not dist:
-                traffic = tr["dram_bytes_per_launch"]
+            if tr and not dist and tr.get("kernel", "").split("<")[0] == kernel_name.split("<")[0]:
+                traffic, traffic_src = tr["dram_bytes_per_launch"], tr.get("source")
         except Exception:
             pass
         roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "kernel": kernel_name, "avg_launch_us": t_push * 1e6,
+                    "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name, "avg_launch_us": t_push * 1e6,
                     "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
                     "frac_of_nominal_8TBs": ach / 8000.0, "push_share_of_step": push_ms / (ms_total if not dist else wall),
                     "resid_kernel_avg_us": (res_ms / res_cnt * 1e3) if res_cnt else None,
@@ -369,13 +395,52 @@ def main():
         e2e_s = float(t.item())
     e2e_value = nnz_total * sum(r.matvec_count for r in e2e_results) / e2e_s
 
-    # sanity of what was timed: the solve converged and ||Ax-b||/||b|| is small (library SpMV, bit-checked in tests)
-    rel_res = None
+    # the same call with PAGEABLE host buffers (what a Rust Vec<f64> caller hands over): staged through the library's
+    # pinned ring
+    e2e_pageable = None
     if not dist:
-        y = torch.empty_like(b_dev)
-        m.multiply_vector_dev(x_dev.data_ptr(), n_local, y.data_ptr(), n_local, False, stream)
-        torch.cuda.synchronize()
-        rel_res = float(torch.linalg.vector_norm(y - b_dev) / torch.linalg.vector_norm(b_dev))
+        b_pg, x_pg = np.array(b, copy=True), np.empty(n_local)
+        solver.solve(m, b_pg, opts, out=x_pg)
+        barrier()
+        t0 = time.perf_counter()
+        pg_results = [solver.solve(m, b_pg, opts, out=x_pg) for _ in range(args.steps)]
+        barrier()
+        e2e_pageable = nnz_total * sum(r.matvec_count for r in pg_results) / (time.perf_counter() - t0)
+
+    # ---- parity of what was timed, against the CPU oracle (the checker, never the timed path): the solution of the last
+    # timed step vs orc_neumann_solve on the same system (bit-exact expected), and ||Ax-b||/||b|| from the ORACLE's SpMV.
+    # N > 1: the rank slices are gathered on rank 0 first.
+    parity = None
+    if not args.no_parity:
+        x_full = x_dev
+        if dist:
+            per = -(-size // world)
+            pad = torch.zeros(per, dtype=torch.float64, device="cuda")
+            pad[:n_local] = x_dev
+            parts = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+            td.gather(pad, parts, dst=0)
+            if rank == 0:
+                x_full = torch.cat(parts)[:size]
+        if rank == 0:
+            from oracle import oracle as O
+            t0 = time.perf_counter()
+            xs = x_full.cpu().numpy()
+            if args.workload.startswith("banded"):
+                rp_, ci_, v_, bo = gen_banded(size, 10, 64)
+                Ao = O.Csr(size, size, v_, ci_, rp_.astype(np.uint32))
+            else:
+                Ao, bo = O.gen_bench_csr(size, sparsity)
+            o = O.neumann_solve(Ao, bo, mode=mode, spmv_variant=O.SPMV_PARALLEL)
+            rres = float(np.linalg.norm(Ao.multiply_vector(xs, O.SPMV_PARALLEL) - bo) / np.linalg.norm(bo))
+            parity = {"oracle": "oracle/sublinear_oracle.c orc_neumann_solve (row-chunk parallel SpMV, scalar order in a row)",
+                      "max_abs_err": float(np.max(np.abs(xs - o.solution))),
+                      "bit_exact": bool(np.array_equal(xs, o.solution)),
+                      "counts_equal": (r_last.iterations, r_last.terms_computed, r_last.matvec_count, bool(r_last.converged)) ==
+                                      (o.iterations, o.terms_computed, o.matvec_count, bool(o.converged)),
+                      "residual_norm": r_last.residual_norm, "oracle_residual_norm": o.residual_norm,
+                      "rel_residual_oracle_spmv": rres, "seconds": time.perf_counter() - t0}
+            del Ao
+    rel_res = parity["rel_residual_oracle_spmv"] if parity else None
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -405,13 +470,14 @@ def main():
                        "parallelism": "single GPU" if not dist else (f"row blocks x{world}, term slice exchanged per term: " +
                                                       ("NCCL allgather + allreduce" if os.environ.get("SUBLINEAR_B200_DIST") == "nccl"
                                                        else "fused peer-memory stores from the push kernel (CUDA IPC over NVLink)")),
-                       "rel_residual": rel_res, "setup_s": t_gen,
+                       "rel_residual": rel_res, "parity": parity, "setup_s": t_gen,
                        "device_layout": {sb.LAYOUT_SELL32: "SELL-32", sb.LAYOUT_CSR_SLABS: "CSR column slabs", sb.LAYOUT_CSR: "CSR"}[layout["layout"]],
                        "value_slots_streamed_per_spmv": layout["slots"], "matrix_device_bytes": layout["device_bytes"]},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_local * world if dist else 8 * n_local,
                     "d2h_bytes_per_step": 8 * n_local * world if dist else 8 * n_local, "ms_per_step": e2e_s / args.steps * 1e3,
-                    "api": "sb200_solve_into (host b -> host x)" if not dist else "sb200_dist_solve (host b_local -> host x_local)"},
+                    "api": "sb200_solve_into (pinned host b -> pinned host x)" if not dist else "sb200_dist_solve (host b_local -> host x_local)",
+                    "pageable_value": e2e_pageable},
             "gpu_launches": launches, "clocks": clocks,
         }
         sys.stdout.flush()

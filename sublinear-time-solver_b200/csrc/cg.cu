@@ -130,7 +130,7 @@ int32_t cg_device(sb200_matrix *m, const double *b_dev, const sb200_cg_config *c
             SB_TRY(launch_cg_vec(va, st));
             va.phase = 2;
             SB_TRY(launch_cg_vec(va, st));
-            launches += 2 + (m->nslabs > 1 ? (uint64_t)m->nslabs : 1);
+            launches += 2 + launches_per_pass(m);
         }
         SB_TRY(read_ctl());
         alive = ws.h_ctl->alive != 0;

@@ -133,7 +133,7 @@ struct PeerExchange {               // all zero = not used (single GPU, or the N
     unsigned long long *flags[kMaxPeers];  // peer p's flag array [world]
 };
 
-constexpr int kMaxSlabs = 4;  // column slabs of the gather source (matrix.cu build_slabs)
+constexpr int kMaxSlabs = 8;  // column slabs of the gather source (matrix.cu build_slabs)
 constexpr uint32_t kLongRow = 1024;    // rows above this length leave the ordered per-lane sums (warp-stream kernel)
 constexpr uint32_t kLongChunk = 8192;  // entries of a long row summed by one CTA of the pre-pass
 
@@ -151,12 +151,18 @@ struct TileKernelArgs {
     const uint32_t *sell_ptr;   // nblocks + 1 slab offsets (slab = 32 slots, one per row of the block)
     const uint32_t *sell_cols;
     const double *sell_vals;
-    // the same matrix split into column slabs (matrix.cu build_slabs): nslabs > 1 -> launch_tile_kernel runs one pass of
-    // the warp-stream kernel per slab over slab-local CSR slices; row sums carry over from pass to pass through `acc`
+    // the same matrix regrouped into column slabs (matrix.cu build_slabs): nslabs > 1 -> launch_tile_kernel runs the fused
+    // slab kernel (kernels_slab.cu): one launch walks slab after slab, the row sums carry over through `acc`.
+    // Entries are stored slab-major in one pair of arrays; inside a slab in CSR order. Per slab s and 32-row block b:
+    // slab_blk[s * (nblocks + 1) + b] = index of the block's first entry, slab_len[s * slab_len_stride + row] = entries of
+    // `row` inside the slab (65535 marks a hub row, summed by the long_rows_* pre-pass)
     int nslabs;
-    const double *slab_vals[kMaxSlabs];
-    const uint32_t *slab_cols[kMaxSlabs];
-    const uint32_t *slab_row_ptr[kMaxSlabs];
+    const double *slab_vals;
+    const uint32_t *slab_cols;
+    const uint32_t *slab_blk;
+    const uint16_t *slab_len;
+    uint64_t slab_len_stride;
+    int acc_keep;               // the carried row sums fit the L2 next to the slab of the vector: do not mark them evict-first
     // rows with more than kLongRow entries (hub rows of power-law graphs): launch_tile_kernel lets the whole grid compute
     // their sums first (kernels.cu long_rows_*), the row-block kernel only looks them up
     uint32_t nlong;             // number of long rows of this matrix (0: none)
@@ -166,8 +172,6 @@ struct TileKernelArgs {
     const uint2 *long_chunks;   // {begin, end} entry ranges of at most kLongChunk entries
     const double *long_sum;     // set by the launcher: (A xin)_row of the long rows, in list order
     double *acc;           // n doubles of scratch for the partial row sums; null: `out` carries them
-    const double *acc_in;  // set per pass by the launcher: continue these sums (null in the first pass)
-    double *acc_out;       // set per pass by the launcher: store the sums instead of running the epilogue (null in the last)
     // vectors
     const double *xin;    // gather source (term / solution / x)
     const double *xin_own; // value of xin for local row i is xin_own[i] (== xin + row_base)
@@ -204,15 +208,22 @@ struct SetupOut {
 };
 int32_t launch_setup_rows(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
                           uint32_t row_base, int compat_diag, SetupOut out, cudaStream_t stream);
-// column-slab split at ingest: counts per (row, slab), then the ordered fill; unsorted[0] receives 1 if some row is not
-// sorted by column (then the split would change the accumulation order and is not used), unsorted[1] the number of
-// rows whose entries fall into more than one slab
+// column-slab split at ingest (warp per 32-row block): entries per (row, slab) as u16 (65535 = hub row, left to the pre-pass)
+// and per (block, slab) as u32; flags[0] receives 1 if some row is not sorted by column (then the split would change the
+// accumulation order and is not used), flags[1] the number of rows whose entries fall into more than one slab. After the
+// prefix sums over blk (per slab, plus the slab's base), the ordered fill.
 int32_t launch_slab_count(const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows, uint32_t slab_width, int nslabs,
-                          uint32_t *const *counts, int *unsorted, cudaStream_t stream);
+                          uint32_t long_row, uint16_t *len, uint64_t len_stride, uint32_t *blk, int *flags,
+                          cudaStream_t stream);
 int32_t launch_slab_fill(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
-                         uint32_t slab_width, int nslabs, const uint32_t *const *slab_row_ptr, uint32_t *const *slab_cols,
-                         double *const *slab_vals, cudaStream_t stream);
+                         uint32_t slab_width, int nslabs, const uint16_t *len, uint64_t len_stride, const uint32_t *blk,
+                         uint32_t *slab_cols, double *slab_vals, cudaStream_t stream);
+int32_t launch_add_u32(uint32_t *data, uint64_t n, uint32_t v, cudaStream_t stream);
+// exclusive prefix sum in place over data[0..n); data[n] and *total receive the sum (multi-CTA: tile sums, scan of the
+// tile sums, tile-local scan)
 int32_t device_exclusive_scan_u32(uint32_t *data, uint64_t n, uint64_t *total, cudaStream_t stream);
+// the fused column-slab kernel (kernels_slab.cu)
+int32_t launch_slab_kernel(Epilogue epi, const TileKernelArgs &a, cudaStream_t stream, int *max_grid_out);
 int32_t launch_csr_to_sell(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
                            const uint32_t *sell_ptr, uint32_t *sell_cols, double *sell_vals, cudaStream_t stream);
 int32_t launch_col_dominance(const double *col_diag, const double *col_off, uint32_t n, unsigned long long *first_bad,

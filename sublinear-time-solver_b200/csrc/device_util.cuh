@@ -253,5 +253,59 @@ __device__ __forceinline__ void grid_reduce_and_tail(double sq, double aux, Loop
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// per-row epilogue shared by the warp-stream, the SELL and the fused column-slab kernel: `acc` = (A xin)_row
+// ---------------------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void row_epilogue(const TileKernelArgs &a, uint32_t row, double acc, double own, double dv,
+                                             double xs, double rh, double &sq, double &aux) {
+    if (EPI == EPI_SPMV) {
+        a.out[row] = acc;
+    } else if (EPI == EPI_PUSH) {
+        const double tmp = acc * dv;   // temp *= d_inv        (neumann.rs:289-291)
+        const double tn = own - tmp;   // term -= temp         (neumann.rs:294-296)
+        a.out[row] = tn;
+        a.sol[row] = xs + tn;          // solution += term     (neumann.rs:264-266)
+        if (a.px.world > 1) {
+            // fused exchange: this rank's slice of the new term (and of x when a residual check follows)
+            // goes straight into every peer's buffers over NVLink, 256 contiguous bytes per warp and peer
+            const size_t g = (size_t)a.row_base + row;
+            for (int p = 0; p < a.px.world; p++) {
+                if (p == a.px.rank || !a.px.t_out[p]) continue;
+                a.px.t_out[p][g] = tn;
+                if (a.px.x_out[p]) a.px.x_out[p][g] = xs + tn;
+            }
+            if (a.px.x_out[a.px.rank]) a.px.x_out[a.px.rank][g] = xs + tn;
+        }
+        sq += tn * tn;                 // l2_norm accumulation (solver/mod.rs:369-371)
+        if (a.identity_res) {
+            const double r = tn / dv;  // (D o t')_i = (b - A x)_i, SURVEY F12
+            aux += r * r;
+        }
+    } else if (EPI == EPI_CG) {
+        a.out[row] = acc;              // ap = A p             (optimized_solver.rs:224)
+        sq += own * acc;               // p^T ap               (optimized_solver.rs:228-232)
+    } else {
+        const double r = acc - rh;     // r = A x - rhs        (neumann.rs:308-310)
+        sq += r * r;
+    }
+}
+
+// per-row operands of the epilogue (coalesced: lane r <-> row r)
+template <int EPI>
+__device__ __forceinline__ void row_operands(const TileKernelArgs &a, uint32_t row, double &own, double &dv, double &xs,
+                                             double &rh) {
+    if (EPI == EPI_PUSH) {
+        own = a.xin[a.row_base + row];
+        dv = a.dinv[row];
+        xs = a.sol[row];
+    } else if (EPI == EPI_RESID) {
+        rh = a.rhs[row];
+    } else if (EPI == EPI_CG) {
+        own = a.xin[a.row_base + row];
+    } else if (a.accumulate) {
+        xs = a.out[row];
+    }
+}
 
 }  // namespace sb200

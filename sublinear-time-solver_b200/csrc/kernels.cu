@@ -27,6 +27,8 @@
 // update, squared norm) is fused; norms are reduced deterministically (fixed-shape tree per CTA or warp, fixed-order
 // sum of the partials by the last CTA) and the last CTA also advances the device-resident loop state (LoopCtl), so the
 // host never has to synchronise per term.
+#include <algorithm>
+
 #include "device_util.cuh"
 
 namespace sb200 {
@@ -77,28 +79,18 @@ static int32_t launch_with_long_rows(Epilogue epi, const TileKernelArgs &a, cuda
     TileKernelArgs p = a;
     p.long_sum = scratch + a.nlong_chunks;
     int32_t rc = cudaGetLastError() == cudaSuccess ? SB200_OK : fail(SB200_ERR_ALGORITHM, "long-row pre-pass launch failed");
-    if (rc == SB200_OK) rc = launch_warp_any(epi, p, stream, nullptr);
+    if (rc == SB200_OK) rc = a.nslabs > 1 ? launch_slab_kernel(epi, p, stream, nullptr) : launch_warp_any(epi, p, stream, nullptr);
     cudaFreeAsync(scratch, stream);
     return rc;
 }
 
 int32_t launch_tile_kernel(int cfg, Epilogue epi, const TileKernelArgs &a, cudaStream_t stream) {
     if (cfg < 0 && a.nslabs > 1) {
-        // column-slab passes: the gather source of one pass is a slab of the vector small enough to stay in the L2
-        // partition of each die; the row sums continue from pass to pass in column = CSR order
-        double *acc = a.acc ? a.acc : a.out;
-        if (!acc) return fail(SB200_ERR_ALGORITHM, "column-slab passes need a buffer for the partial row sums");
-        for (int s = 0; s < a.nslabs; s++) {
-            TileKernelArgs p = a;
-            p.vals = a.slab_vals[s];
-            p.cols = a.slab_cols[s];
-            p.row_ptr = a.slab_row_ptr[s];
-            p.sell_ptr = nullptr;
-            p.acc_in = s > 0 ? acc : nullptr;
-            p.acc_out = s + 1 < a.nslabs ? acc : nullptr;
-            SB_TRY(launch_warp_any(epi, p, stream, nullptr));
-        }
-        return SB200_OK;
+        // column slabs: the gather source of one phase is a slab of the vector small enough to stay in the L2 partition of
+        // each die; one fused launch, the row sums continue from slab to slab in column = CSR order
+        if (!a.acc && !a.out) return fail(SB200_ERR_ALGORITHM, "column-slab passes need a buffer for the partial row sums");
+        if (a.nlong > 0) return launch_with_long_rows(epi, a, stream);
+        return launch_slab_kernel(epi, a, stream, nullptr);
     }
     if (cfg < 0 && a.sell_ptr != nullptr) return launch_sell_any(epi, a, stream, nullptr);
     if (cfg < 0 && a.nlong > 0) return launch_with_long_rows(epi, a, stream);
@@ -114,65 +106,11 @@ int tile_kernel_max_grid(int cfg, Epilogue epi) {
     int mg = 0;
     TileKernelArgs dummy{};
     if (cfg >= 0) return launch_tile_pipeline(cfg, epi, dummy, nullptr, &mg) == SB200_OK ? mg : 0;
-    int ms = 0;
+    int ms = 0, mf = 0;
     if (launch_warp_any(epi, dummy, nullptr, &mg) != SB200_OK) return 0;
     if (launch_sell_any(epi, dummy, nullptr, &ms) != SB200_OK) return 0;  // one partial per warp
-    return mg > ms ? mg : ms;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// per-row epilogue shared by the warp-stream and the SELL kernel: `acc` = (A xin)_row
-// ---------------------------------------------------------------------------------------------------------
-template <int EPI>
-__device__ __forceinline__ void row_epilogue(const TileKernelArgs &a, uint32_t row, double acc, double own, double dv,
-                                             double xs, double rh, double &sq, double &aux) {
-    if (EPI == EPI_SPMV) {
-        a.out[row] = acc;
-    } else if (EPI == EPI_PUSH) {
-        const double tmp = acc * dv;   // temp *= d_inv        (neumann.rs:289-291)
-        const double tn = own - tmp;   // term -= temp         (neumann.rs:294-296)
-        a.out[row] = tn;
-        a.sol[row] = xs + tn;          // solution += term     (neumann.rs:264-266)
-        if (a.px.world > 1) {
-            // fused exchange: this rank's slice of the new term (and of x when a residual check follows)
-            // goes straight into every peer's buffers over NVLink, 256 contiguous bytes per warp and peer
-            const size_t g = (size_t)a.row_base + row;
-            for (int p = 0; p < a.px.world; p++) {
-                if (p == a.px.rank || !a.px.t_out[p]) continue;
-                a.px.t_out[p][g] = tn;
-                if (a.px.x_out[p]) a.px.x_out[p][g] = xs + tn;
-            }
-            if (a.px.x_out[a.px.rank]) a.px.x_out[a.px.rank][g] = xs + tn;
-        }
-        sq += tn * tn;                 // l2_norm accumulation (solver/mod.rs:369-371)
-        if (a.identity_res) {
-            const double r = tn / dv;  // (D o t')_i = (b - A x)_i, SURVEY F12
-            aux += r * r;
-        }
-    } else if (EPI == EPI_CG) {
-        a.out[row] = acc;              // ap = A p             (optimized_solver.rs:224)
-        sq += own * acc;               // p^T ap               (optimized_solver.rs:228-232)
-    } else {
-        const double r = acc - rh;     // r = A x - rhs        (neumann.rs:308-310)
-        sq += r * r;
-    }
-}
-
-// per-row operands of the epilogue (coalesced: lane r <-> row r)
-template <int EPI>
-__device__ __forceinline__ void row_operands(const TileKernelArgs &a, uint32_t row, double &own, double &dv, double &xs,
-                                             double &rh) {
-    if (EPI == EPI_PUSH) {
-        own = a.xin[a.row_base + row];
-        dv = a.dinv[row];
-        xs = a.sol[row];
-    } else if (EPI == EPI_RESID) {
-        rh = a.rhs[row];
-    } else if (EPI == EPI_CG) {
-        own = a.xin[a.row_base + row];
-    } else if (a.accumulate) {
-        xs = a.out[row];
-    }
+    if (launch_slab_kernel(epi, dummy, nullptr, &mf) != SB200_OK) return 0;
+    return std::max(mg, std::max(ms, mf));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -216,11 +154,8 @@ __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
         const uint32_t b0 = __shfl_sync(0xffffffffu, rs, 0);
         const uint32_t b1 = __shfl_sync(0xffffffffu, re, (int)(rlast & 31u));
         double own = 0.0, dv = 0.0, xs = 0.0, rh = 0.0;
-        // column-slab passes (launch_tile_kernel): only the last pass runs the epilogue, the others hand the running
-        // row sums on through acc_out -> acc_in; the order of the additions is the single-pass order
-        if (active && (a.acc_out == nullptr || (EPI == EPI_SPMV && a.acc_in == nullptr))) row_operands<EPI>(a, row, own, dv, xs, rh);
+        if (active) row_operands<EPI>(a, row, own, dv, xs, rh);
         double acc = (EPI == EPI_SPMV && a.accumulate) ? xs : 0.0;
-        if (a.acc_in != nullptr) acc = active ? ld_once_f64_hint(a.acc_in + row, pol_stream) : 0.0;  // used once: evict first
         const uint32_t max_len = __reduce_max_sync(0xffffffffu, re - rs);
         if (max_len <= kLongRow) {
             for (uint32_t c0 = b0 & ~(uint32_t)(EPL - 1); c0 < b1; c0 += CH) {
@@ -292,12 +227,9 @@ __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
                 if ((uint32_t)lane == i) acc += part;
             }
         }
-        if (active) {
-            if (a.acc_out != nullptr) st_stream_f64_hint(a.acc_out + row, acc, pol_stream);  // keep the slab of x in L2
-            else row_epilogue<EPI>(a, row, acc, own, dv, xs, rh, sq, aux);
-        }
+        if (active) row_epilogue<EPI>(a, row, acc, own, dv, xs, rh, sq, aux);
     }
-    if (EPI != EPI_SPMV && a.acc_out == nullptr) {
+    if (EPI != EPI_SPMV) {
         const int kind = EPI == EPI_PUSH ? TAIL_TERM : (EPI == EPI_CG ? TAIL_CG_PAP : TAIL_RESID);
         grid_reduce_and_tail<NT>(sq, aux, a.ctl, a.partials, kind, a.it, a.last_in_iter, a.identity_res, a.defer_tail,
                                  a.norm_log, s_red, &s_flag, &a.px);

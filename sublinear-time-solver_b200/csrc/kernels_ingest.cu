@@ -40,131 +40,234 @@ int32_t launch_csr_to_sell(const double *vals, const uint32_t *cols, const uint3
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// column-slab split at ingest (one-off; matrix.cu build_slabs)
+// column-slab split at ingest (one-off; matrix.cu build_slabs). Warp per 32-row block, lane r <-> row r.
 // ---------------------------------------------------------------------------------------------------------
-struct SlabPtrs {
-    uint32_t *counts[kMaxSlabs];
-    const uint32_t *row_ptr[kMaxSlabs];
-    uint32_t *cols[kMaxSlabs];
-    double *vals[kMaxSlabs];
-};
-
-__global__ void slab_count_kernel(const uint32_t *__restrict__ cols, const uint32_t *__restrict__ row_ptr, uint32_t nrows,
-                                  uint32_t slab_width, int nslabs, SlabPtrs p, int *unsorted) {
-    for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += gridDim.x * blockDim.x) {
-        uint32_t cnt[kMaxSlabs] = {0u, 0u, 0u, 0u};
-        uint32_t prev = 0;
-        bool bad = false;
-        for (uint32_t k = row_ptr[row]; k < row_ptr[row + 1]; k++) {
-            const uint32_t c = cols[k];
-            bad |= c < prev;
-            prev = c;
-            const uint32_t s = min(c / slab_width, (uint32_t)(nslabs - 1));
-            cnt[s]++;
+__global__ void __launch_bounds__(256) slab_count_kernel(const uint32_t *__restrict__ cols, const uint32_t *__restrict__ row_ptr,
+                                                         uint32_t nrows, uint32_t slab_width, int nslabs, uint32_t long_row,
+                                                         uint16_t *__restrict__ len, uint64_t len_stride,
+                                                         uint32_t *__restrict__ blk, int *flags) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t nblocks = (nrows + 31u) >> 5, nb1 = nblocks + 1u;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < nblocks; b += nwarps) {
+        const uint32_t row = (b << 5) + lane;
+        uint32_t cnt[kMaxSlabs];
+#pragma unroll
+        for (int s = 0; s < kMaxSlabs; s++) cnt[s] = 0u;
+        bool is_long = false;
+        if (row < nrows) {
+            const uint32_t rs = row_ptr[row], re = row_ptr[row + 1];
+            is_long = re - rs > long_row;
+            uint32_t prev = 0;
+            bool bad = false;
+            for (uint32_t k = rs; k < re; k++) {
+                const uint32_t c = cols[k];
+                bad |= c < prev;
+                prev = c;
+                const uint32_t s = min(c / slab_width, (uint32_t)(nslabs - 1));
+#pragma unroll
+                for (int q = 0; q < kMaxSlabs; q++) cnt[q] += (uint32_t)(q == (int)s);
+            }
+            int used = 0;
+#pragma unroll
+            for (int s = 0; s < kMaxSlabs; s++) used += cnt[s] != 0u;
+            if (bad) flags[0] = 1;
+            if (used > 1) atomicAdd(flags + 1, 1);  // rows whose gathers spread over several slabs
         }
-        int used = 0;
-        for (int s = 0; s < nslabs; s++) {
-            p.counts[s][row] = cnt[s];
-            used += cnt[s] != 0u;
+#pragma unroll
+        for (int s = 0; s < kMaxSlabs; s++) {
+            if (s >= nslabs) break;
+            const uint32_t c = is_long ? 0u : cnt[s];  // hub rows keep their entries in the CSR slices only
+            if (row < nrows) len[(size_t)s * len_stride + row] = is_long ? (uint16_t)65535 : (uint16_t)c;
+            const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0) blk[(size_t)s * nb1 + b] = tot;
         }
-        if (bad) unsorted[0] = 1;
-        if (used > 1) atomicAdd(unsorted + 1, 1);  // rows whose gathers spread over several slabs
     }
 }
 
-__global__ void slab_fill_kernel(const double *__restrict__ vals, const uint32_t *__restrict__ cols,
-                                 const uint32_t *__restrict__ row_ptr, uint32_t nrows, uint32_t slab_width, int nslabs,
-                                 SlabPtrs p) {
-    for (uint32_t row = blockIdx.x * blockDim.x + threadIdx.x; row < nrows; row += gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(256) slab_fill_kernel(const double *__restrict__ vals, const uint32_t *__restrict__ cols,
+                                                        const uint32_t *__restrict__ row_ptr, uint32_t nrows,
+                                                        uint32_t slab_width, int nslabs, const uint16_t *__restrict__ len,
+                                                        uint64_t len_stride, const uint32_t *__restrict__ blk,
+                                                        uint32_t *__restrict__ sc, double *__restrict__ sv) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t nblocks = (nrows + 31u) >> 5, nb1 = nblocks + 1u;
+    const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < nblocks; b += nwarps) {
+        const uint32_t row = (b << 5) + lane;
         uint32_t pos[kMaxSlabs];
-        for (int s = 0; s < nslabs; s++) pos[s] = p.row_ptr[s][row];
+        bool is_long = false;
+#pragma unroll
+        for (int s = 0; s < kMaxSlabs; s++) {
+            pos[s] = 0u;
+            if (s >= nslabs) continue;
+            uint32_t l = row < nrows ? len[(size_t)s * len_stride + row] : 0u;
+            if (l == 65535u) { is_long = true; l = 0u; }
+            uint32_t incl = l;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            pos[s] = blk[(size_t)s * nb1 + b] + incl - l;
+        }
+        if (row >= nrows || is_long) continue;
         for (uint32_t k = row_ptr[row]; k < row_ptr[row + 1]; k++) {  // in CSR order: the order inside a slab row is kept
             const uint32_t c = cols[k];
+            const double v = vals[k];
             const uint32_t s = min(c / slab_width, (uint32_t)(nslabs - 1));
-            p.cols[s][pos[s]] = c;
-            p.vals[s][pos[s]] = vals[k];
-            pos[s]++;
+            uint32_t p = 0;
+#pragma unroll
+            for (int q = 0; q < kMaxSlabs; q++)
+                if (q == (int)s) { p = pos[q]; pos[q]++; }
+            sc[p] = c;
+            sv[p] = v;
         }
     }
+}
+
+static unsigned block_grid(uint32_t nrows) {
+    const uint32_t nblocks = (nrows + 31u) / 32u;
+    unsigned grid = (nblocks + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    return grid ? grid : 1;
 }
 
 int32_t launch_slab_count(const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows, uint32_t slab_width, int nslabs,
-                          uint32_t *const *counts, int *unsorted, cudaStream_t stream) {
-    SlabPtrs p{};
-    for (int s = 0; s < nslabs; s++) p.counts[s] = counts[s];
-    unsigned grid = (nrows + 255) / 256;
-    if (grid > 148 * 16) grid = 148 * 16;
-    if (grid == 0) grid = 1;
-    slab_count_kernel<<<grid, 256, 0, stream>>>(cols, row_ptr, nrows, slab_width, nslabs, p, unsorted);
+                          uint32_t long_row, uint16_t *len, uint64_t len_stride, uint32_t *blk, int *flags,
+                          cudaStream_t stream) {
+    slab_count_kernel<<<block_grid(nrows), 256, 0, stream>>>(cols, row_ptr, nrows, slab_width, nslabs, long_row, len,
+                                                             len_stride, blk, flags);
     SB_CUDA(cudaGetLastError());
     return SB200_OK;
 }
 
 int32_t launch_slab_fill(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
-                         uint32_t slab_width, int nslabs, const uint32_t *const *slab_row_ptr, uint32_t *const *slab_cols,
-                         double *const *slab_vals, cudaStream_t stream) {
-    SlabPtrs p{};
-    for (int s = 0; s < nslabs; s++) {
-        p.row_ptr[s] = slab_row_ptr[s];
-        p.cols[s] = slab_cols[s];
-        p.vals[s] = slab_vals[s];
-    }
-    unsigned grid = (nrows + 255) / 256;
-    if (grid > 148 * 16) grid = 148 * 16;
-    if (grid == 0) grid = 1;
-    slab_fill_kernel<<<grid, 256, 0, stream>>>(vals, cols, row_ptr, nrows, slab_width, nslabs, p);
+                         uint32_t slab_width, int nslabs, const uint16_t *len, uint64_t len_stride, const uint32_t *blk,
+                         uint32_t *slab_cols, double *slab_vals, cudaStream_t stream) {
+    slab_fill_kernel<<<block_grid(nrows), 256, 0, stream>>>(vals, cols, row_ptr, nrows, slab_width, nslabs, len, len_stride,
+                                                            blk, slab_cols, slab_vals);
     SB_CUDA(cudaGetLastError());
     return SB200_OK;
 }
 
-// exclusive prefix sum of n u32 counts in place (data has n + 1 entries: data[n] receives the total), single CTA:
-// an ingest-time helper, not a hot path (10 M rows: ~1 ms)
-__global__ void __launch_bounds__(1024) exclusive_scan_u32_kernel(uint32_t *data, uint64_t n, unsigned long long *total) {
-    __shared__ unsigned long long s_warp[32];
-    __shared__ unsigned long long s_carry;
+__global__ void add_u32_kernel(uint32_t *data, uint64_t n, uint32_t v) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) data[i] += v;
+}
+
+int32_t launch_add_u32(uint32_t *data, uint64_t n, uint32_t v, cudaStream_t stream) {
+    if (n == 0 || v == 0) return SB200_OK;
+    uint64_t g = (n + 255) / 256;
+    add_u32_kernel<<<(unsigned)(g > 148ull * 8 ? 148ull * 8 : g), 256, 0, stream>>>(data, n, v);
+    SB_CUDA(cudaGetLastError());
+    return SB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// exclusive prefix sum of n u32 counts in place (data has n + 1 entries: data[n] receives the total). Three launches over
+// tiles of 4096 elements: per-tile sums, a one-CTA scan of the (<= a few thousand) tile sums, tile-local scans + the tile's
+// base. Sums are carried in 64 bits; the stored offsets are u32 (callers check the total).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanPer = 16;                       // consecutive elements per thread
+constexpr uint64_t kScanTile = (uint64_t)kScanThreads * kScanPer;
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan_u64(unsigned long long v, unsigned long long *s_warp,
+                                                                      unsigned long long *total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0ull;
+    unsigned long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();  // s_warp may still be read from a previous call
+    if (lane == 31) s_warp[warp] = x;
     __syncthreads();
-    for (uint64_t base = 0; base < n; base += 1024) {
-        const uint64_t i = base + threadIdx.x;
-        const unsigned long long v = i < n ? data[i] : 0ull;
-        unsigned long long x = v;
+    if (warp == 0) {
+        unsigned long long w = lane < (int)(blockDim.x >> 5) ? s_warp[lane] : 0ull;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
         }
-        if (lane == 31) s_warp[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = s_warp[lane];
+        s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    if (total) *total = s_warp[(blockDim.x >> 5) - 1];
+    return (warp ? s_warp[warp - 1] : 0ull) + (x - v);
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t *__restrict__ data, uint64_t n,
+                                                                      unsigned long long *__restrict__ tile_sums) {
+    __shared__ unsigned long long s_warp[32];
+    const uint64_t base = blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPer;
+    unsigned long long v = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            s_warp[lane] = w;  // inclusive over warps
-        }
+    for (int q = 0; q < kScanPer; q++)
+        if (base + q < n) v += data[base + q];
+    unsigned long long tot;
+    block_exclusive_scan_u64(v, s_warp, &tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// one CTA: exclusive scan of the tile sums in place; tile_sums[ntiles] receives the grand total
+__global__ void __launch_bounds__(1024) scan_tile_bases_kernel(unsigned long long *tile_sums, uint64_t ntiles) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0ull;
+    __syncthreads();
+    for (uint64_t base = 0; base < ntiles; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const unsigned long long v = i < ntiles ? tile_sums[i] : 0ull;
+        unsigned long long tot;
+        const unsigned long long ex = block_exclusive_scan_u64(v, s_warp, &tot);
+        const unsigned long long carry = s_carry;
+        if (i < ntiles) tile_sums[i] = carry + ex;
         __syncthreads();
-        const unsigned long long before = s_carry + (warp ? s_warp[warp - 1] : 0ull) + (x - v);
-        if (i < n) data[i] = (uint32_t)before;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = before + v;
+        if (threadIdx.x == 0) s_carry = carry + tot;
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
-        data[n] = (uint32_t)s_carry;
-        *total = s_carry;
+    if (threadIdx.x == 0) tile_sums[ntiles] = s_carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t *__restrict__ data, uint64_t n,
+                                                                  const unsigned long long *__restrict__ tile_sums,
+                                                                  uint64_t ntiles) {
+    __shared__ unsigned long long s_warp[32];
+    const uint64_t base = blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanPer;
+    uint32_t e[kScanPer];
+    unsigned long long v = 0;
+#pragma unroll
+    for (int q = 0; q < kScanPer; q++) {
+        e[q] = base + q < n ? data[base + q] : 0u;
+        v += e[q];
     }
+    unsigned long long run = tile_sums[blockIdx.x] + block_exclusive_scan_u64(v, s_warp, nullptr);
+#pragma unroll
+    for (int q = 0; q < kScanPer; q++) {
+        if (base + q < n) data[base + q] = (uint32_t)run;
+        run += e[q];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) data[n] = (uint32_t)tile_sums[ntiles];
 }
 
 int32_t device_exclusive_scan_u32(uint32_t *data, uint64_t n, uint64_t *total, cudaStream_t stream) {
+    const uint64_t ntiles = (n + kScanTile - 1) / kScanTile;
+    if (ntiles > 0x7FFFFFFFull) return fail(SB200_ERR_INVALID_INPUT, "prefix sum over %llu elements", (unsigned long long)n);
     DevBuf<unsigned long long> t;
-    SB_TRY(t.alloc(1));
-    exclusive_scan_u32_kernel<<<1, 1024, 0, stream>>>(data, n, t.p);
-    SB_CUDA(cudaGetLastError());
+    SB_TRY(t.alloc(ntiles + 1));
+    if (ntiles == 0) {
+        SB_CUDA(cudaMemsetAsync(t.p, 0, 8, stream));
+        SB_CUDA(cudaMemsetAsync(data, 0, 4, stream));
+    } else {
+        scan_tile_sums_kernel<<<(unsigned)ntiles, kScanThreads, 0, stream>>>(data, n, t.p);
+        scan_tile_bases_kernel<<<1, 1024, 0, stream>>>(t.p, ntiles);
+        scan_apply_kernel<<<(unsigned)ntiles, kScanThreads, 0, stream>>>(data, n, t.p, ntiles);
+        SB_CUDA(cudaGetLastError());
+    }
     unsigned long long h = 0;
-    SB_CUDA(cudaMemcpyAsync(&h, t.p, 8, cudaMemcpyDeviceToHost, stream));
+    SB_CUDA(cudaMemcpyAsync(&h, t.p + ntiles, 8, cudaMemcpyDeviceToHost, stream));
     SB_CUDA(cudaStreamSynchronize(stream));
     if (total) *total = h;
     return SB200_OK;

@@ -24,11 +24,10 @@ sb200_matrix::~sb200_matrix() {
     d_long_rows.release();
     d_long_first.release();
     d_long_chunks.release();
-    for (int s = 0; s < sb200::kMaxSlabs; s++) {
-        d_slab_vals[s].release();
-        d_slab_cols[s].release();
-        d_slab_row_ptr[s].release();
-    }
+    d_slab_vals.release();
+    d_slab_cols.release();
+    d_slab_blk.release();
+    d_slab_len.release();
     d_dinv[0].release();
     d_dinv[1].release();
     if (stream) cudaStreamDestroy(stream);
@@ -145,16 +144,17 @@ static int32_t build_sell(sb200_matrix *m) {
     return SB200_OK;
 }
 
-// Hub rows: rows with more than kLongRow entries get a chunk table so that the whole grid can sum them before the
+// Hub rows: rows with more than `threshold` entries get a chunk table so that the whole grid can sum them before the
 // row-block kernel runs (kernels.cu long_rows_*). O(n) over the host row_ptr copy.
 static int32_t build_long_rows(sb200_matrix *m) {
+    const uint32_t threshold = kLongRow;
     m->nlong = m->nlong_chunks = 0;
     const uint32_t *rp = m->h_row_ptr.data();
     std::vector<uint32_t> rows, first;
     std::vector<uint2> chunks;
     for (uint64_t r = 0; r < m->nrows; r++) {
         const uint32_t rs = rp[r], re = rp[r + 1];
-        if (re - rs <= kLongRow) continue;
+        if (re - rs <= threshold) continue;
         rows.push_back((uint32_t)r);
         first.push_back((uint32_t)chunks.size());
         for (uint64_t s = rs; s < re; s += kLongChunk)
@@ -174,18 +174,19 @@ static int32_t build_long_rows(sb200_matrix *m) {
     return SB200_OK;
 }
 
-// Column-slab split for the hot kernels. Measured on a B200 (profiles/r1_slab_timing.log): random 8-byte
+// Column-slab layout for the hot kernels. Measured on a B200 (profiles/r1_slab_timing.log): random 8-byte
 // gathers cost one L2 sector operation while the gather source fits the L2 partition of each die (<= ~40 MB) and 2.4
 // once it does not (80 MB: every far-homed line is looked up near, fetched over the fabric and filled again), and the
-// push kernel runs at the chip's L2 sector-throughput cap. Splitting the columns into slabs of <= 28 MB of the vector and
-// running one pass per slab keeps the gathers at one operation each; rows are column-sorted, so carrying the row sum
-// from slab to slab adds the products in exactly the CSR order.
-// $SUBLINEAR_B200_SLABS = 0 forbids, 2..4 forces that many slabs; default: matrices (and the row blocks of the multi-GPU
-// path, whose gather source is the full-length vector) whose gathered vector is > 48 MB and <= 4 * 42 MB. Needs every row sorted by column (checked on the device), otherwise the split is dropped.
+// push kernel runs at the chip's L2 sector-throughput cap. Regrouping the entries into column slabs of <= 28 MB of the
+// vector and walking slab after slab keeps the gathers at one operation each; rows are column-sorted, so carrying the
+// row sum from slab to slab adds the products in exactly the CSR order.
+// $SUBLINEAR_B200_SLABS = 0 forbids, 2..8 forces that many slabs. Default: the gathered vector is > 48 MB and <= 8 * 28 MB
+// and the matrix holds enough entries per vector sector for the window to pay (a row block of the multi-GPU path gathers
+// from the full-length vector with only its share of the entries: $SUBLINEAR_B200_SLAB_MIN_DENSITY entries per 32-byte
+// sector of the vector, default 2). Needs every row sorted by column (checked on the device), otherwise the split is dropped.
 static int32_t build_slabs(sb200_matrix *m) {
     m->nslabs = 0;
     if (m->tile_cfg >= 0 || m->nrows == 0 || m->nnz == 0) return SB200_OK;
-    if (m->nlong > 0) return SB200_OK;  // hub rows are summed by the single-pass pre-pass (per-slab chunk tables: not yet)
     const char *e = getenv("SUBLINEAR_B200_SLABS");
     const int force = e ? atoi(e) : -1;
     if (force == 0 || force == 1) return SB200_OK;
@@ -195,60 +196,62 @@ static int32_t build_slabs(sb200_matrix *m) {
         S = force > kMaxSlabs ? kMaxSlabs : force;
         if ((uint64_t)S > m->ncols) return SB200_OK;
     } else {
-        if (vec_bytes <= 48e6 || vec_bytes > 4 * 42e6) return SB200_OK;
+        if (vec_bytes <= 48e6 || vec_bytes > kMaxSlabs * 28e6) return SB200_OK;
+        const char *d = getenv("SUBLINEAR_B200_SLAB_MIN_DENSITY");
+        const double min_density = d ? atof(d) : 2.0;
+        if ((double)m->nnz < min_density * vec_bytes / 32.0) return SB200_OK;
         S = (int)std::ceil(vec_bytes / 28e6);
         if (S > kMaxSlabs) S = kMaxSlabs;
     }
     const uint32_t width = (uint32_t)((m->ncols + S - 1) / S);
-    const uint64_t n = m->nrows;
-    DevBuf<int> d_unsorted;
-    SB_TRY(d_unsorted.alloc(2));
-    SB_CUDA(cudaMemsetAsync(d_unsorted.p, 0, 2 * sizeof(int), m->stream));
-    uint32_t *counts[kMaxSlabs] = {nullptr, nullptr, nullptr, nullptr};
-    for (int s = 0; s < S; s++) {
-        SB_TRY(m->d_slab_row_ptr[s].alloc(n + 1));
-        counts[s] = m->d_slab_row_ptr[s].p;
-    }
-    SB_TRY(launch_slab_count(m->d_cols.p, m->d_row_ptr.p, (uint32_t)n, width, S, counts, d_unsorted.p, m->stream));
+    const uint64_t n = m->nrows, nblocks = (n + 31) / 32, nb1 = nblocks + 1;
+    const uint64_t len_stride = (n + 127) & ~127ull;
+    DevBuf<int> d_flags;
+    SB_TRY(d_flags.alloc(2));
+    SB_CUDA(cudaMemsetAsync(d_flags.p, 0, 2 * sizeof(int), m->stream));
+    SB_TRY(m->d_slab_blk.alloc((size_t)S * nb1));
+    SB_TRY(m->d_slab_len.alloc((size_t)S * len_stride));
+    SB_CUDA(cudaMemsetAsync(m->d_slab_len.p, 0, (size_t)S * len_stride * sizeof(uint16_t), m->stream));
+    SB_TRY(launch_slab_count(m->d_cols.p, m->d_row_ptr.p, (uint32_t)n, width, S, kLongRow, m->d_slab_len.p, len_stride,
+                             m->d_slab_blk.p, d_flags.p, m->stream));
     int flags[2] = {0, 0};
-    SB_CUDA(cudaMemcpyAsync(flags, d_unsorted.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    SB_CUDA(cudaMemcpyAsync(flags, d_flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     SB_CUDA(cudaStreamSynchronize(m->stream));
     const int unsorted = flags[0];
     // banded / block-local matrices gather from a window of the vector that stays cached anyway: extra passes would
-    // only add row_ptr and partial-sum traffic. Split only when most rows really reach into several slabs.
+    // only add hand-over traffic. Split only when most rows really reach into several slabs.
     const bool local = force < 2 && (uint64_t)flags[1] * 2 < n;
-    auto drop = [&]() {
-        for (int s = 0; s < kMaxSlabs; s++) {
-            m->d_slab_row_ptr[s].release();
-            m->d_slab_cols[s].release();
-            m->d_slab_vals[s].release();
-            m->slab_nnz[s] = 0;
-        }
-    };
     if (unsorted || local) {  // unsorted rows (from_csr input): the split would reorder the sums
-        drop();
+        m->d_slab_blk.release();
+        m->d_slab_len.release();
         return SB200_OK;
     }
-    uint32_t *scols[kMaxSlabs] = {nullptr, nullptr, nullptr, nullptr};
-    double *svals[kMaxSlabs] = {nullptr, nullptr, nullptr, nullptr};
-    const uint32_t *srp[kMaxSlabs] = {nullptr, nullptr, nullptr, nullptr};
+    // per-slab prefix sums over the block counts, then the slab bases (multiples of 4 entries: 32-byte aligned value loads)
+    uint64_t base = 0;
     for (int s = 0; s < S; s++) {
         uint64_t total = 0;
-        SB_TRY(device_exclusive_scan_u32(m->d_slab_row_ptr[s].p, n, &total, m->stream));
-        m->slab_nnz[s] = total;
-        const size_t pad = ((total + 3) & ~(size_t)3) + 8;  // same over-read slack as the CSR slices
-        SB_TRY(m->d_slab_cols[s].alloc(pad));
-        SB_TRY(m->d_slab_vals[s].alloc(pad));
-        SB_CUDA(cudaMemsetAsync(m->d_slab_cols[s].p + total, 0, (pad - total) * sizeof(uint32_t), m->stream));
-        SB_CUDA(cudaMemsetAsync(m->d_slab_vals[s].p + total, 0, (pad - total) * sizeof(double), m->stream));
-        scols[s] = m->d_slab_cols[s].p;
-        svals[s] = m->d_slab_vals[s].p;
-        srp[s] = m->d_slab_row_ptr[s].p;
+        uint32_t *blk = m->d_slab_blk.p + (size_t)s * nb1;
+        SB_TRY(device_exclusive_scan_u32(blk, nblocks, &total, m->stream));
+        if (base + total >= 0xFFFFFFF0ull) {
+            m->d_slab_blk.release();
+            m->d_slab_len.release();
+            return SB200_OK;
+        }
+        SB_TRY(launch_add_u32(blk, nb1, (uint32_t)base, m->stream));
+        base = (base + total + 3) & ~3ull;
     }
-    SB_TRY(launch_slab_fill(m->d_vals.p, m->d_cols.p, m->d_row_ptr.p, (uint32_t)n, width, S, srp, scols, svals, m->stream));
+    const size_t entries = base + 8;  // over-read slack of the last chunk
+    SB_TRY(m->d_slab_cols.alloc(entries));
+    SB_TRY(m->d_slab_vals.alloc(entries));
+    SB_CUDA(cudaMemsetAsync(m->d_slab_cols.p, 0, entries * sizeof(uint32_t), m->stream));  // padding: column 0, value 0
+    SB_CUDA(cudaMemsetAsync(m->d_slab_vals.p, 0, entries * sizeof(double), m->stream));
+    SB_TRY(launch_slab_fill(m->d_vals.p, m->d_cols.p, m->d_row_ptr.p, (uint32_t)n, width, S, m->d_slab_len.p, len_stride,
+                            m->d_slab_blk.p, m->d_slab_cols.p, m->d_slab_vals.p, m->stream));
     SB_CUDA(cudaStreamSynchronize(m->stream));
     m->nslabs = S;
     m->slab_width = width;
+    m->slab_len_stride = len_stride;
+    m->slab_entries = entries;
     return SB200_OK;
 }
 
@@ -323,8 +326,8 @@ int32_t matrix_from_host_csr(const uint64_t *row_ptr64, const uint32_t *row_ptr3
     SB_TRY(copy_h2d(m->d_cols.p, cols, nnz * sizeof(uint32_t), m->stream));
     SB_TRY(copy_h2d(m->d_row_ptr.p, rp, (nrows + 1) * sizeof(uint32_t), m->stream));
     SB_TRY(copy_h2d(m->d_tiles.p, tiles.data(), tiles.size() * sizeof(TileDesc), m->stream));
-    SB_TRY(build_long_rows(m.get()));
     if (allow_slabs) SB_TRY(build_slabs(m.get()));
+    SB_TRY(build_long_rows(m.get()));
     if (m->nslabs == 0) SB_TRY(build_sell(m.get()));
     SB_CUDA(cudaStreamSynchronize(m->stream));
     *out = m.release();
@@ -347,11 +350,12 @@ void fill_tile_args(const sb200_matrix *m, TileKernelArgs &a) {
     a.long_chunks = m->d_long_chunks.p;
     a.long_sum = nullptr;
     a.nslabs = m->nslabs;
-    for (int s = 0; s < m->nslabs; s++) {
-        a.slab_vals[s] = m->d_slab_vals[s].p;
-        a.slab_cols[s] = m->d_slab_cols[s].p;
-        a.slab_row_ptr[s] = m->d_slab_row_ptr[s].p;
-    }
+    a.slab_vals = m->d_slab_vals.p;
+    a.slab_cols = m->d_slab_cols.p;
+    a.slab_blk = m->d_slab_blk.p;
+    a.slab_len = m->d_slab_len.p;
+    a.slab_len_stride = m->slab_len_stride;
+    a.acc_keep = m->nrows * 16 <= (24ull << 20);  // carried sums small enough to live in L2 next to the slab window
     a.nrows = (uint32_t)m->nrows;
     a.row_base = (uint32_t)m->row_base;
     a.xin_len = m->ncols;
@@ -599,8 +603,7 @@ int32_t sb200_matrix_storage_info(const sb200_matrix *m, int32_t *layout, uint64
         uint64_t b = m->d_vals.n * 8 + m->d_cols.n * 4 + m->d_row_ptr.n * 4 + m->d_tiles.n * sizeof(TileDesc) +
                      m->d_sell_ptr.n * 4 + m->d_sell_cols.n * 4 + m->d_sell_vals.n * 8 + m->d_dinv[0].n * 8 +
                      m->d_dinv[1].n * 8;
-        for (int s = 0; s < kMaxSlabs; s++)
-            b += m->d_slab_vals[s].n * 8 + m->d_slab_cols[s].n * 4 + m->d_slab_row_ptr[s].n * 4;
+        b += m->d_slab_vals.n * 8 + m->d_slab_cols.n * 4 + m->d_slab_blk.n * 4 + m->d_slab_len.n * 2;
         *device_bytes = b;
     }
     return SB200_OK;
@@ -714,7 +717,7 @@ int32_t sb200_matrix_scale(sb200_matrix *m, double factor) {
     DeviceGuard g(m->device);
     SB_TRY(launch_scale(m->d_vals.p, m->nnz, factor, m->stream));
     if (m->use_sell) SB_TRY(launch_scale(m->d_sell_vals.p, m->sell_slabs * 32, factor, m->stream));
-    for (int s = 0; s < m->nslabs; s++) SB_TRY(launch_scale(m->d_slab_vals[s].p, m->slab_nnz[s], factor, m->stream));
+    if (m->nslabs > 1) SB_TRY(launch_scale(m->d_slab_vals.p, m->slab_entries, factor, m->stream));
     SB_CUDA(cudaStreamSynchronize(m->stream));
     std::lock_guard<std::mutex> lk(m->mu);
     m->analysed[0] = m->analysed[1] = m->col_analysed = false;  // cached D^-1 is stale

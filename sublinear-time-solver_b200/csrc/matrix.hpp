@@ -53,15 +53,18 @@ struct sb200_matrix {
     uint32_t nlong = 0, nlong_chunks = 0;
     sb200::DevBuf<uint32_t> d_long_rows, d_long_first;
     sb200::DevBuf<uint2> d_long_chunks;
-    // column-slab split for the hot kernels (kernels.cu launch_tile_kernel): when the gather source (8 * ncols bytes) does
-    // not fit the L2 partition of a die, the entries are regrouped into nslabs column ranges of slab_width columns, each
-    // with its own CSR slices; one kernel pass per slab, row sums carried over in column order (bit-identical results)
+    // column-slab layout for the hot kernels (kernels_slab.cu): when the gather source (8 * ncols bytes) does not fit the
+    // L2 partition of a die, the entries are regrouped into nslabs column ranges of slab_width columns, stored slab-major
+    // in one pair of arrays (CSR order inside a slab); per slab a u32 entry offset per 32-row block and a u16 length per
+    // row. One fused launch walks the slabs, row sums carried over in column order (bit-identical results)
     int nslabs = 0;
     uint32_t slab_width = 0;
-    sb200::DevBuf<double> d_slab_vals[sb200::kMaxSlabs];
-    sb200::DevBuf<uint32_t> d_slab_cols[sb200::kMaxSlabs];
-    sb200::DevBuf<uint32_t> d_slab_row_ptr[sb200::kMaxSlabs];
-    uint64_t slab_nnz[sb200::kMaxSlabs] = {0, 0, 0, 0};
+    sb200::DevBuf<double> d_slab_vals;
+    sb200::DevBuf<uint32_t> d_slab_cols;
+    sb200::DevBuf<uint32_t> d_slab_blk;   // nslabs * (nblocks + 1)
+    sb200::DevBuf<uint16_t> d_slab_len;    // nslabs * slab_len_stride
+    uint64_t slab_len_stride = 0;
+    uint64_t slab_entries = 0;            // entries stored in the slab arrays (incl. alignment padding between slabs)
     cudaStream_t stream = nullptr;  // for host-pointer entry points
 
     // distributed: this handle holds rows [row_base, row_base + nrows) of an n_global-square system
@@ -97,6 +100,8 @@ void matrix_release(sb200_matrix *m);  // deletes the handle when the last owner
 std::unique_ptr<Workspace> matrix_acquire_ws(sb200_matrix *m);
 void matrix_release_ws(sb200_matrix *m, std::unique_ptr<Workspace> ws);
 void fill_tile_args(const sb200_matrix *m, TileKernelArgs &a);
+// kernel launches of one pass over the matrix: the hub-row pre-pass (2 launches) precedes the row kernel where it applies
+inline uint64_t launches_per_pass(const sb200_matrix *m) { return m->nlong > 0 && !m->use_sell ? 3 : 1; }
 
 struct DeviceGuard {
     int prev = -1;

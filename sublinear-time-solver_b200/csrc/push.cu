@@ -148,7 +148,7 @@ int32_t push_run(const sb200_push_graph *g, const sb200_push_config *cfg, const 
         visited += h[1];
         rounds++;
         SB_TRY(matrix_spmv_dev(M, d_carry.p, d_r.p, 1, st));  // r += M carry
-        launches += M->nslabs > 1 ? (uint64_t)M->nslabs : 1;
+        launches += launches_per_pass(M);
     }
     SB_CUDA(cudaEventRecord(e1, st));
     SB_TRY(copy_d2h(est_out, d_est.p, n * 8, st));

@@ -59,8 +59,7 @@ int32_t solve_device(const sb200_solver *s, sb200_matrix *m, const double *b_dev
     SB_CUDA(cudaMemcpyAsync(ws.ctl.p, ws.h_ctl, sizeof(LoopCtl), cudaMemcpyHostToDevice, st));
 
     uint64_t launches = 0, extra_matvec = 0;
-    // kernel launches per pass over the matrix: one per column slab, or pre-pass (2) + row-block kernel for hub rows
-    const uint64_t kpl = m->nslabs > 1 ? (uint64_t)m->nslabs : (m->nlong > 0 && !m->use_sell ? 3 : 1);
+    const uint64_t kpl = launches_per_pass(m);
     const double *dinv = m->d_dinv[opt->mode].p;
     const double *resid_rhs = compat ? ws.c.p : b_dev;  // update_residual subtracts D^-1 b in the reference (:308-314)
 
