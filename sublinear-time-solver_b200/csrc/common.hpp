@@ -154,14 +154,14 @@ struct TileKernelArgs {
     // the same matrix regrouped into column slabs (matrix.cu build_slabs): nslabs > 1 -> launch_tile_kernel runs the fused
     // slab kernel (kernels_slab.cu): one launch walks slab after slab, the row sums carry over through `acc`.
     // Entries are stored slab-major in one pair of arrays; inside a slab in CSR order. Per slab s and 32-row block b:
-    // slab_blk[s * (nblocks + 1) + b] = index of the block's first entry, slab_len[s * slab_len_stride + row] = entries of
-    // `row` inside the slab (65535 marks a hub row, summed by the long_rows_* pre-pass)
+    // slab_blk[s * (nblocks + 1) + b] = index of the block's first entry, slab_rel[s * slab_rel_stride + row] = offset of
+    // the row's first entry inside its block (u16; bit 15 marks a hub row, summed by the long_rows_* pre-pass)
     int nslabs;
     const double *slab_vals;
     const uint32_t *slab_cols;
     const uint32_t *slab_blk;
-    const uint16_t *slab_len;
-    uint64_t slab_len_stride;
+    const uint16_t *slab_rel;
+    uint64_t slab_rel_stride;
     int acc_keep;               // the carried row sums fit the L2 next to the slab of the vector: do not mark them evict-first
     // rows with more than kLongRow entries (hub rows of power-law graphs): launch_tile_kernel lets the whole grid compute
     // their sums first (kernels.cu long_rows_*), the row-block kernel only looks them up
@@ -208,15 +208,15 @@ struct SetupOut {
 };
 int32_t launch_setup_rows(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
                           uint32_t row_base, int compat_diag, SetupOut out, cudaStream_t stream);
-// column-slab split at ingest (warp per 32-row block): entries per (row, slab) as u16 (65535 = hub row, left to the pre-pass)
-// and per (block, slab) as u32; flags[0] receives 1 if some row is not sorted by column (then the split would change the
+// column-slab split at ingest (warp per 32-row block): per (row, slab) the u16 offset of the row's first entry inside its
+// block (bit 15 = hub row, left to the pre-pass) and per (block, slab) the u32 entry count; flags[0] receives 1 if some row is not sorted by column (then the split would change the
 // accumulation order and is not used), flags[1] the number of rows whose entries fall into more than one slab. After the
 // prefix sums over blk (per slab, plus the slab's base), the ordered fill.
 int32_t launch_slab_count(const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows, uint32_t slab_width, int nslabs,
-                          uint32_t long_row, uint16_t *len, uint64_t len_stride, uint32_t *blk, int *flags,
+                          uint32_t long_row, uint16_t *rel, uint64_t rel_stride, uint32_t *blk, int *flags,
                           cudaStream_t stream);
 int32_t launch_slab_fill(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
-                         uint32_t slab_width, int nslabs, const uint16_t *len, uint64_t len_stride, const uint32_t *blk,
+                         uint32_t slab_width, int nslabs, const uint16_t *rel, uint64_t rel_stride, const uint32_t *blk,
                          uint32_t *slab_cols, double *slab_vals, cudaStream_t stream);
 int32_t launch_add_u32(uint32_t *data, uint64_t n, uint32_t v, cudaStream_t stream);
 // exclusive prefix sum in place over data[0..n); data[n] and *total receive the sum (multi-CTA: tile sums, scan of the

@@ -166,7 +166,21 @@ int32_t ensure_arena(sb200_comm *c, uint64_t nfull) {
     cudaError_t e = cudaMalloc(&A.base, bytes);
     if (e != cudaSuccess) {
         A.base = nullptr;
-        return fail(SB200_ERR_MEMORY_ALLOCATION, "cudaMalloc of the %zu-byte exchange arena failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    {   // every rank learns whether any allocation failed before anybody waits in the handle exchange
+        const double mine_failed = e != cudaSuccess ? 1.0 : 0.0;
+        double any = 0.0;
+        SB_CUDA(cudaMemcpyAsync(bar.p, &mine_failed, 8, cudaMemcpyHostToDevice, st));
+        SB_NCCL(g_nccl.AllReduce(bar.p, bar.p, 1, ncclDouble, ncclMax, c->comm, st));
+        SB_CUDA(cudaMemcpyAsync(&any, bar.p, 8, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        if (any != 0.0) {
+            if (A.base) cudaFree(A.base);
+            A.base = nullptr;
+            return fail(SB200_ERR_MEMORY_ALLOCATION, "cudaMalloc of the %zu-byte exchange arena failed on %s: %s", bytes,
+                        e != cudaSuccess ? "this rank" : "another rank", cudaGetErrorString(e));
+        }
     }
     SB_CUDA(cudaMemset(A.base, 0, bytes));
     SB_CUDA(cudaDeviceSynchronize());
@@ -434,24 +448,31 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
     clear_error();
     if (!out) return fail(SB200_ERR_INVALID_INPUT, "result is null");
     memset(out, 0, sizeof(*out));
-    if (!s) return fail(SB200_ERR_INVALID_INPUT, "null solver");
-    SB_TRY(validate_options(opt));
-    if (opt->initial_guess) return fail(SB200_ERR_INVALID_INPUT, "initial_guess is not supported by sb200_dist_solve yet");
-    if (opt->dominance != SB200_DOMINANCE_ROW)
-        return fail(SB200_ERR_INVALID_INPUT, "column dominance needs whole columns: not available on a row block");
-    DistPlan p;
-    SB_TRY(dist_check(c, m, nlocal, p));
-    if (nlocal && (!b_local || !x_local)) return fail(SB200_ERR_INVALID_INPUT, "null vector");
+    // without a communicator / matrix nothing can be agreed on: these are the only rank-local returns. Every other
+    // precondition is folded into local_rc and returned only after agree_status(), so that a rank that rejects its
+    // arguments never leaves the others blocked in a collective or spinning on its flags.
+    if (!c || !m) return fail(SB200_ERR_INVALID_INPUT, "null comm or matrix");
     DeviceGuard g(m->device);
     sb200_matrix *mm = const_cast<sb200_matrix *>(m);
     cudaStream_t st = c->stream;
-    const bool compat = opt->mode == SB200_MODE_REF_COMPAT;
-    const bool identity = opt->residual_check == SB200_RESIDUAL_IDENTITY;
+    DistPlan p;
+    int32_t local_rc = SB200_OK;
+    auto check = [&](int32_t rc) { if (local_rc == SB200_OK) local_rc = rc; };
+    if (!s) check(fail(SB200_ERR_INVALID_INPUT, "null solver"));
+    else check(validate_options(opt));
+    if (local_rc == SB200_OK) check(dist_check(c, m, nlocal, p));
+    if (local_rc == SB200_OK && nlocal && (!b_local || !x_local)) check(fail(SB200_ERR_INVALID_INPUT, "null vector"));
+    if (local_rc == SB200_OK && opt->initial_guess && opt->initial_guess_len != nlocal)
+        check(fail(SB200_ERR_DIMENSION_MISMATCH, "expected %llu, actual %llu in initial_guess (local rows)",
+                   (unsigned long long)nlocal, (unsigned long long)opt->initial_guess_len));
+    const uint64_t max_it = (opt && local_rc == SB200_OK) ? opt->max_iterations : 1, max_terms = s ? s->max_terms : 1;
+    if (local_rc == SB200_OK && (max_it >= 0xFFFFFFFFull || max_terms >= 0xFFFFFFFFull || max_it == 0 || max_terms == 0))
+        check(fail(SB200_ERR_INVALID_INPUT, "max_iterations / max_terms must be in [1, 2^32)"));
+    const bool args_ok = local_rc == SB200_OK;
+    const bool compat = args_ok && opt->mode == SB200_MODE_REF_COMPAT;
+    const bool identity = args_ok && opt->residual_check == SB200_RESIDUAL_IDENTITY;
     const bool multi = c->world > 1;
     const bool p2p = multi && c->p2p;
-    const uint64_t max_it = opt->max_iterations, max_terms = s->max_terms;
-    if (max_it >= 0xFFFFFFFFull || max_terms >= 0xFFFFFFFFull || max_it == 0 || max_terms == 0)
-        return fail(SB200_ERR_INVALID_INPUT, "max_iterations / max_terms must be in [1, 2^32)");
 
     auto ws = matrix_acquire_ws(mm);
     struct Release {
@@ -462,24 +483,56 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
     const int cfg = m->tile_cfg;
     const size_t npart = 2 * (size_t)std::max(std::max(tile_kernel_max_grid(cfg, EPI_PUSH), tile_kernel_max_grid(cfg, EPI_RESID)),
                                               init_state_grid()) + 2;
-    SB_TRY(ws->ensure(p.nloc, p2p ? 1 : p.per * c->world, npart));
+    if (args_ok) check(ws->ensure(p.nloc, p2p ? 1 : p.per * c->world, npart));
+    else SB_TRY(ws->ensure(1, 1, 4));  // the agreement below only needs one scratch double
+    {
+        const int32_t rc = agree_status(c, local_rc, *ws, st);
+        if (rc != SB200_OK) return local_rc != SB200_OK ? local_rc : fail(rc, "another rank rejected its arguments");
+    }
     if (p2p) {
-        SB_TRY(ensure_arena(c, p.per * c->world));
+        SB_TRY(ensure_arena(c, p.per * c->world));  // collective; allocation failures are agreed on inside
         c->epoch_base += 1ull << 24;  // a fresh epoch range per solve
     }
     // term ping-pong and the full-length solution mirror: arena vectors (P2P) or workspace buffers (NCCL)
     double *const T[2] = {p2p ? c->arena.vec(c->rank, 0) : ws->t[0].p, p2p ? c->arena.vec(c->rank, 1) : ws->t[1].p};
 
-    // local checks of NeumannState::new, then agree across ranks so that nobody blocks in a collective
-    int32_t local_rc = matrix_analyse(mm, opt->mode, false);
-    if (local_rc == SB200_OK && m->first_bad_dd != kNone)
+    // local checks of NeumannState::new, then agree across ranks so that nobody blocks in a collective. Column
+    // dominance (SB200_DOMINANCE_ROW_OR_COL, the PageRank systems) needs whole columns: the per-column sums of the row
+    // blocks are all-reduced before the test, and "row dominant" has to hold on every rank.
+    const bool cols = opt->dominance == SB200_DOMINANCE_ROW_OR_COL;
+    ColReduce reduce_cols;
+    if (cols && multi)
+        reduce_cols = [&](double *cd, double *co, uint64_t nc, cudaStream_t s2) -> int32_t {
+            SB_NCCL(g_nccl.GroupStart());
+            SB_NCCL(g_nccl.AllReduce(cd, cd, nc, ncclDouble, ncclSum, c->comm, s2));
+            SB_NCCL(g_nccl.AllReduce(co, co, nc, ncclDouble, ncclSum, c->comm, s2));
+            SB_NCCL(g_nccl.GroupEnd());
+            return SB200_OK;
+        };
+    local_rc = matrix_analyse(mm, opt->mode, cols, reduce_cols);
+    if (cols) {
+        // 2 = a row of this block violates row dominance; the column verdict is already global
+        const int32_t any_bad_row = agree_status(c, (local_rc == SB200_OK && m->first_bad_dd != kNone) ? 2 : 0, *ws, st);
+        if (local_rc == SB200_OK && any_bad_row != 0 && m->first_bad_col != kNone)
+            local_rc = fail(SB200_ERR_MATRIX_NOT_DIAGONALLY_DOMINANT,
+                            "matrix is neither row nor column diagonally dominant (first violating column %llu)",
+                            (unsigned long long)m->first_bad_col);
+    } else if (local_rc == SB200_OK && m->first_bad_dd != kNone) {
         local_rc = fail(SB200_ERR_MATRIX_NOT_DIAGONALLY_DOMINANT, "matrix is not diagonally dominant (first violating row %llu)",
                         (unsigned long long)(m->first_bad_dd + p.row0));
+    }
     if (local_rc == SB200_OK && m->first_bad_diag[opt->mode] != kNone)
         local_rc = fail(SB200_ERR_INVALID_SPARSE_MATRIX, "Missing or near-zero diagonal element at position %llu",
                         (unsigned long long)(m->first_bad_diag[opt->mode] + p.row0));
-    const int32_t rc = agree_status(c, local_rc, *ws, st);
-    if (rc != SB200_OK) return local_rc != SB200_OK ? local_rc : fail(rc, "another rank rejected its row block");
+    DevBuf<double> x0;
+    if (local_rc == SB200_OK && opt->initial_guess) {
+        local_rc = x0.alloc(p.nloc);
+        if (local_rc == SB200_OK) local_rc = copy_h2d(x0.p, opt->initial_guess, p.nloc * 8, st);
+    }
+    {
+        const int32_t rc = agree_status(c, local_rc, *ws, st);
+        if (rc != SB200_OK) return local_rc != SB200_OK ? local_rc : fail(rc, "another rank rejected its row block");
+    }
 
     SB_TRY(copy_h2d(ws->b.p, b_local, p.nloc * 8, st));
     LoopCtl h{};
@@ -561,9 +614,39 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
     } prof_cleanup{prof};
     const bool profiling = opt->enable_profiling != 0;
 
+    // initial guess (local rows). ref_compat: x = x0 + c, the series still starts from c (neumann.rs:197-211).
+    // correct: t0 = D^-1 (b - A x0) needs all of x0 on every rank: the slices are exchanged into the term buffer that
+    // stays dead until iteration 1 writes it, then one SpMV over the local rows.
+    uint64_t extra_matvec = 0;
+    const double *ax0 = nullptr;
+    if (x0.p && !compat) {
+        const double *x0full = x0.p - p.row0;
+        if (p2p) {
+            double *dst[kMaxPeers];
+            for (int q = 0; q < c->world; q++) dst[q] = c->arena.vec(q, 1);
+            SB_TRY(launch_peer_publish(x0.p, p.nloc, p.row0, dst, ws->ctl.p, make_px(c, -1, false), 1, st));
+            SB_TRY(peer_wait(c, ws->ctl.p, 0, 0, 0, 0, 1, nullptr, st));
+            x0full = T[1];
+        } else if (multi) {
+            SB_CUDA(cudaMemcpyAsync(T[1] + p.row0, x0.p, p.nloc * 8, cudaMemcpyDeviceToDevice, st));
+            SB_NCCL(g_nccl.AllGather(T[1] + (uint64_t)c->rank * p.per, T[1], p.per, ncclDouble, c->comm, st));
+            x0full = T[1];
+        }
+        TileKernelArgs a{};
+        fill_tile_args(m, a);
+        a.xin = x0full;
+        a.xin_own = x0.p;
+        a.out = ws->tmp.p;
+        SB_TRY(launch_tile_kernel(cfg, EPI_SPMV, a, st));
+        ax0 = ws->tmp.p;
+        extra_matvec = 1;
+    }
+
     SB_CUDA(cudaEventRecord(ws->ev0, st));
     {
         InitArgs ia{};
+        ia.x0 = x0.p;
+        ia.ax0 = ax0;
         ia.b = ws->b.p;
         ia.dinv = dinv;
         ia.c_out = ws->c.p;
@@ -681,7 +764,7 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
         const uint64_t counted = std::min<uint64_t>(cc.iterations, iterations);
         loop_resids = counted ? (counted - 1) / 5 + 1 : 0;
     }
-    stt.matvec = (cc.terms > 0 ? cc.terms - 1 : 0) + loop_resids + resid_in_loop + 1;
+    stt.matvec = (cc.terms > 0 ? cc.terms - 1 : 0) + loop_resids + resid_in_loop + 1 + extra_matvec;
     stt.converged = (stt.residual_norm <= opt->tolerance) || (stt.series_converged && cc.terms < max_terms);
 
     out->residual_norm = stt.residual_norm;
@@ -695,7 +778,7 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
     out->memory_bytes = ws->bytes();
     out->matvec_count = stt.matvec;
     out->has_stats = opt->collect_stats != 0;
-    out->h2d_bytes = p.nloc * 8;
+    out->h2d_bytes = p.nloc * 8 * (x0.p ? 2 : 1);
     out->d2h_bytes = p.nloc * 8;
     for (auto &q : prof) {
         if (q.it >= cc.terms) continue;  // launches past the end of the loop were no-ops

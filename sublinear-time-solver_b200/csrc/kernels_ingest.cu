@@ -44,7 +44,7 @@ int32_t launch_csr_to_sell(const double *vals, const uint32_t *cols, const uint3
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) slab_count_kernel(const uint32_t *__restrict__ cols, const uint32_t *__restrict__ row_ptr,
                                                          uint32_t nrows, uint32_t slab_width, int nslabs, uint32_t long_row,
-                                                         uint16_t *__restrict__ len, uint64_t len_stride,
+                                                         uint16_t *__restrict__ rel, uint64_t rel_stride,
                                                          uint32_t *__restrict__ blk, int *flags) {
     const int lane = threadIdx.x & 31;
     const uint32_t nblocks = (nrows + 31u) >> 5, nb1 = nblocks + 1u;
@@ -78,8 +78,16 @@ __global__ void __launch_bounds__(256) slab_count_kernel(const uint32_t *__restr
         for (int s = 0; s < kMaxSlabs; s++) {
             if (s >= nslabs) break;
             const uint32_t c = is_long ? 0u : cnt[s];  // hub rows keep their entries in the CSR slices only
-            if (row < nrows) len[(size_t)s * len_stride + row] = is_long ? (uint16_t)65535 : (uint16_t)c;
-            const uint32_t tot = __reduce_add_sync(0xffffffffu, c);
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            // offset of the row's first entry inside the block (< 32 * kLongRow = 2^15), bit 15 marks a hub row; lanes
+            // past the last row store the block total, i.e. an empty row
+            rel[(size_t)s * rel_stride + row] = (uint16_t)((incl - c) | (is_long ? 0x8000u : 0u));
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
             if (lane == 0) blk[(size_t)s * nb1 + b] = tot;
         }
     }
@@ -87,8 +95,8 @@ __global__ void __launch_bounds__(256) slab_count_kernel(const uint32_t *__restr
 
 __global__ void __launch_bounds__(256) slab_fill_kernel(const double *__restrict__ vals, const uint32_t *__restrict__ cols,
                                                         const uint32_t *__restrict__ row_ptr, uint32_t nrows,
-                                                        uint32_t slab_width, int nslabs, const uint16_t *__restrict__ len,
-                                                        uint64_t len_stride, const uint32_t *__restrict__ blk,
+                                                        uint32_t slab_width, int nslabs, const uint16_t *__restrict__ rel,
+                                                        uint64_t rel_stride, const uint32_t *__restrict__ blk,
                                                         uint32_t *__restrict__ sc, double *__restrict__ sv) {
     const int lane = threadIdx.x & 31;
     const uint32_t nblocks = (nrows + 31u) >> 5, nb1 = nblocks + 1u;
@@ -101,15 +109,9 @@ __global__ void __launch_bounds__(256) slab_fill_kernel(const double *__restrict
         for (int s = 0; s < kMaxSlabs; s++) {
             pos[s] = 0u;
             if (s >= nslabs) continue;
-            uint32_t l = row < nrows ? len[(size_t)s * len_stride + row] : 0u;
-            if (l == 65535u) { is_long = true; l = 0u; }
-            uint32_t incl = l;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += y;
-            }
-            pos[s] = blk[(size_t)s * nb1 + b] + incl - l;
+            const uint32_t r = rel[(size_t)s * rel_stride + row];
+            is_long |= (r & 0x8000u) != 0u;
+            pos[s] = blk[(size_t)s * nb1 + b] + (r & 0x7FFFu);
         }
         if (row >= nrows || is_long) continue;
         for (uint32_t k = row_ptr[row]; k < row_ptr[row + 1]; k++) {  // in CSR order: the order inside a slab row is kept
@@ -134,18 +136,18 @@ static unsigned block_grid(uint32_t nrows) {
 }
 
 int32_t launch_slab_count(const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows, uint32_t slab_width, int nslabs,
-                          uint32_t long_row, uint16_t *len, uint64_t len_stride, uint32_t *blk, int *flags,
+                          uint32_t long_row, uint16_t *rel, uint64_t rel_stride, uint32_t *blk, int *flags,
                           cudaStream_t stream) {
-    slab_count_kernel<<<block_grid(nrows), 256, 0, stream>>>(cols, row_ptr, nrows, slab_width, nslabs, long_row, len,
-                                                             len_stride, blk, flags);
+    slab_count_kernel<<<block_grid(nrows), 256, 0, stream>>>(cols, row_ptr, nrows, slab_width, nslabs, long_row, rel,
+                                                             rel_stride, blk, flags);
     SB_CUDA(cudaGetLastError());
     return SB200_OK;
 }
 
 int32_t launch_slab_fill(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
-                         uint32_t slab_width, int nslabs, const uint16_t *len, uint64_t len_stride, const uint32_t *blk,
+                         uint32_t slab_width, int nslabs, const uint16_t *rel, uint64_t rel_stride, const uint32_t *blk,
                          uint32_t *slab_cols, double *slab_vals, cudaStream_t stream) {
-    slab_fill_kernel<<<block_grid(nrows), 256, 0, stream>>>(vals, cols, row_ptr, nrows, slab_width, nslabs, len, len_stride,
+    slab_fill_kernel<<<block_grid(nrows), 256, 0, stream>>>(vals, cols, row_ptr, nrows, slab_width, nslabs, rel, rel_stride,
                                                             blk, slab_cols, slab_vals);
     SB_CUDA(cudaGetLastError());
     return SB200_OK;

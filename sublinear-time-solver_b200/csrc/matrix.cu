@@ -27,7 +27,7 @@ sb200_matrix::~sb200_matrix() {
     d_slab_vals.release();
     d_slab_cols.release();
     d_slab_blk.release();
-    d_slab_len.release();
+    d_slab_rel.release();
     d_dinv[0].release();
     d_dinv[1].release();
     if (stream) cudaStreamDestroy(stream);
@@ -205,14 +205,14 @@ static int32_t build_slabs(sb200_matrix *m) {
     }
     const uint32_t width = (uint32_t)((m->ncols + S - 1) / S);
     const uint64_t n = m->nrows, nblocks = (n + 31) / 32, nb1 = nblocks + 1;
-    const uint64_t len_stride = (n + 127) & ~127ull;
+    const uint64_t len_stride = (n + 127) & ~127ull;  // >= 32 * nblocks: every lane of the last block has a slot
     DevBuf<int> d_flags;
     SB_TRY(d_flags.alloc(2));
     SB_CUDA(cudaMemsetAsync(d_flags.p, 0, 2 * sizeof(int), m->stream));
     SB_TRY(m->d_slab_blk.alloc((size_t)S * nb1));
-    SB_TRY(m->d_slab_len.alloc((size_t)S * len_stride));
-    SB_CUDA(cudaMemsetAsync(m->d_slab_len.p, 0, (size_t)S * len_stride * sizeof(uint16_t), m->stream));
-    SB_TRY(launch_slab_count(m->d_cols.p, m->d_row_ptr.p, (uint32_t)n, width, S, kLongRow, m->d_slab_len.p, len_stride,
+    SB_TRY(m->d_slab_rel.alloc((size_t)S * len_stride));
+    SB_CUDA(cudaMemsetAsync(m->d_slab_rel.p, 0, (size_t)S * len_stride * sizeof(uint16_t), m->stream));
+    SB_TRY(launch_slab_count(m->d_cols.p, m->d_row_ptr.p, (uint32_t)n, width, S, kLongRow, m->d_slab_rel.p, len_stride,
                              m->d_slab_blk.p, d_flags.p, m->stream));
     int flags[2] = {0, 0};
     SB_CUDA(cudaMemcpyAsync(flags, d_flags.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, m->stream));
@@ -223,7 +223,7 @@ static int32_t build_slabs(sb200_matrix *m) {
     const bool local = force < 2 && (uint64_t)flags[1] * 2 < n;
     if (unsorted || local) {  // unsorted rows (from_csr input): the split would reorder the sums
         m->d_slab_blk.release();
-        m->d_slab_len.release();
+        m->d_slab_rel.release();
         return SB200_OK;
     }
     // per-slab prefix sums over the block counts, then the slab bases (multiples of 4 entries: 32-byte aligned value loads)
@@ -234,7 +234,7 @@ static int32_t build_slabs(sb200_matrix *m) {
         SB_TRY(device_exclusive_scan_u32(blk, nblocks, &total, m->stream));
         if (base + total >= 0xFFFFFFF0ull) {
             m->d_slab_blk.release();
-            m->d_slab_len.release();
+            m->d_slab_rel.release();
             return SB200_OK;
         }
         SB_TRY(launch_add_u32(blk, nb1, (uint32_t)base, m->stream));
@@ -245,12 +245,12 @@ static int32_t build_slabs(sb200_matrix *m) {
     SB_TRY(m->d_slab_vals.alloc(entries));
     SB_CUDA(cudaMemsetAsync(m->d_slab_cols.p, 0, entries * sizeof(uint32_t), m->stream));  // padding: column 0, value 0
     SB_CUDA(cudaMemsetAsync(m->d_slab_vals.p, 0, entries * sizeof(double), m->stream));
-    SB_TRY(launch_slab_fill(m->d_vals.p, m->d_cols.p, m->d_row_ptr.p, (uint32_t)n, width, S, m->d_slab_len.p, len_stride,
+    SB_TRY(launch_slab_fill(m->d_vals.p, m->d_cols.p, m->d_row_ptr.p, (uint32_t)n, width, S, m->d_slab_rel.p, len_stride,
                             m->d_slab_blk.p, m->d_slab_cols.p, m->d_slab_vals.p, m->stream));
     SB_CUDA(cudaStreamSynchronize(m->stream));
     m->nslabs = S;
     m->slab_width = width;
-    m->slab_len_stride = len_stride;
+    m->slab_rel_stride = len_stride;
     m->slab_entries = entries;
     return SB200_OK;
 }
@@ -353,8 +353,8 @@ void fill_tile_args(const sb200_matrix *m, TileKernelArgs &a) {
     a.slab_vals = m->d_slab_vals.p;
     a.slab_cols = m->d_slab_cols.p;
     a.slab_blk = m->d_slab_blk.p;
-    a.slab_len = m->d_slab_len.p;
-    a.slab_len_stride = m->slab_len_stride;
+    a.slab_rel = m->d_slab_rel.p;
+    a.slab_rel_stride = m->slab_rel_stride;
     a.acc_keep = m->nrows * 16 <= (24ull << 20);  // carried sums small enough to live in L2 next to the slab window
     a.nrows = (uint32_t)m->nrows;
     a.row_base = (uint32_t)m->row_base;
@@ -372,7 +372,7 @@ int32_t matrix_spmv_dev(const sb200_matrix *m, const double *x_dev, double *y_de
 }
 
 // K4, cached per mode. mode 1 (ref_compat) extracts the diagonal like CSRStorage::get, mode 0 sums duplicates.
-int32_t matrix_analyse(sb200_matrix *m, int mode, bool need_cols) {
+int32_t matrix_analyse(sb200_matrix *m, int mode, bool need_cols, const ColReduce &reduce_cols) {
     std::lock_guard<std::mutex> lk(m->mu);
     const bool have = m->analysed[mode] && (!need_cols || m->col_analysed);
     if (have) return SB200_OK;
@@ -398,6 +398,7 @@ int32_t matrix_analyse(sb200_matrix *m, int mode, bool need_cols) {
     }
     SB_TRY(launch_setup_rows(m->d_vals.p, m->d_cols.p, m->d_row_ptr.p, (uint32_t)n, (uint32_t)m->row_base,
                              mode == SB200_MODE_REF_COMPAT, o, m->stream));
+    if (need_cols && reduce_cols) SB_TRY(reduce_cols(col_diag.p, col_off.p, m->ncols, m->stream));
     if (need_cols) SB_TRY(launch_col_dominance(col_diag.p, col_off.p, (uint32_t)m->ncols, scal.p + 2, m->stream));
     unsigned long long res[4];
     SB_CUDA(cudaMemcpyAsync(res, scal.p, sizeof(res), cudaMemcpyDeviceToHost, m->stream));
@@ -603,7 +604,7 @@ int32_t sb200_matrix_storage_info(const sb200_matrix *m, int32_t *layout, uint64
         uint64_t b = m->d_vals.n * 8 + m->d_cols.n * 4 + m->d_row_ptr.n * 4 + m->d_tiles.n * sizeof(TileDesc) +
                      m->d_sell_ptr.n * 4 + m->d_sell_cols.n * 4 + m->d_sell_vals.n * 8 + m->d_dinv[0].n * 8 +
                      m->d_dinv[1].n * 8;
-        b += m->d_slab_vals.n * 8 + m->d_slab_cols.n * 4 + m->d_slab_blk.n * 4 + m->d_slab_len.n * 2;
+        b += m->d_slab_vals.n * 8 + m->d_slab_cols.n * 4 + m->d_slab_blk.n * 4 + m->d_slab_rel.n * 2;
         *device_bytes = b;
     }
     return SB200_OK;

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <atomic>
+#include <functional>
 #include <memory>
 
 #include "common.hpp"
@@ -62,8 +63,8 @@ struct sb200_matrix {
     sb200::DevBuf<double> d_slab_vals;
     sb200::DevBuf<uint32_t> d_slab_cols;
     sb200::DevBuf<uint32_t> d_slab_blk;   // nslabs * (nblocks + 1)
-    sb200::DevBuf<uint16_t> d_slab_len;    // nslabs * slab_len_stride
-    uint64_t slab_len_stride = 0;
+    sb200::DevBuf<uint16_t> d_slab_rel;    // nslabs * slab_rel_stride
+    uint64_t slab_rel_stride = 0;
     uint64_t slab_entries = 0;            // entries stored in the slab arrays (incl. alignment padding between slabs)
     cudaStream_t stream = nullptr;  // for host-pointer entry points
 
@@ -93,7 +94,10 @@ namespace sb200 {
 int32_t matrix_from_host_csr(const uint64_t *row_ptr64, const uint32_t *row_ptr32, const uint32_t *cols,
                              const double *vals, uint64_t nrows, uint64_t ncols, uint64_t nnz, bool validate,
                              sb200_matrix **out, bool allow_slabs = true);
-int32_t matrix_analyse(sb200_matrix *m, int mode, bool need_cols);
+// reduce_cols (row-partitioned handles): sums the per-column |diagonal| and off-diagonal accumulators over all ranks
+// before the column-dominance test, so that every rank sees whole columns
+using ColReduce = std::function<int32_t(double *col_diag, double *col_off, uint64_t ncols, cudaStream_t st)>;
+int32_t matrix_analyse(sb200_matrix *m, int mode, bool need_cols, const ColReduce &reduce_cols = ColReduce());
 int32_t matrix_spmv_dev(const sb200_matrix *m, const double *x_dev, double *y_dev, int accumulate, cudaStream_t st);
 void matrix_retain(sb200_matrix *m);
 void matrix_release(sb200_matrix *m);  // deletes the handle when the last owner lets go
