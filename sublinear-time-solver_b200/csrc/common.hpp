@@ -257,10 +257,6 @@ int32_t launch_update_rhs(const uint64_t *idx, const double *delta, uint64_t cou
 // distributed: finish the loop logic after the partial norms were all-reduced (kind: 1 = term, 2 = residual)
 int32_t launch_dist_tail(LoopCtl *ctl, int kind, uint32_t it, int last_in_iter, int identity_res, int force,
                          double *norm_log, cudaStream_t stream);
-// P2P exchange: wait for all ranks' flags of the current exchange, sum their partials, run the loop logic
-int32_t launch_peer_wait(LoopCtl *ctl, const unsigned long long *flags_local, const double *slots_local, int world,
-                         unsigned long long epoch_base, int kind, uint32_t it, int last_in_iter, int identity_res,
-                         int force, double *norm_log, cudaStream_t stream);
 // conjugate gradient vector passes (kernels_vec.cu). phase 0: x = 0, r = p = b, rsold = b.b ; phase 1: x += alpha p,
 // r -= alpha ap, rsnew = r.r (then beta, rsold, iteration count and the loop decision in the tail) ; phase 2: p = r + beta p
 struct CgVecArgs {

@@ -215,6 +215,37 @@ __device__ __forceinline__ void peer_signal(const LoopCtl *ctl, const PeerExchan
     for (int p = 0; p < px.world; p++) st_release_sys_u64(px.flags[p] + px.rank, e);
 }
 
+// P2P consume, run by the thread that just signalled (the last CTA of a kernel): wait until every rank has raised its flag
+// for the current exchange, add the ranks' partial sums in rank order (every rank computes the same bits) and run the loop
+// logic on the global sums. Folding the wait into the producing kernel saves the separate one-warp wait launch per
+// exchange (round 1: ~5 launches per term at G = 8). No circular wait: a rank signals exchange k before it waits for it,
+// and its kernel k only started after every rank had signalled k - 1.
+__device__ __forceinline__ void peer_consume(LoopCtl *c, const PeerExchange &px, int kind, uint32_t it, int last_in_iter,
+                                             int identity_res, double *norm_log) {
+    const unsigned long long e = px.epoch_base + c->xchg + 1ull;
+    const unsigned long long *flags = px.flags[px.rank];
+    const long long t0 = clock64();
+    for (int r = 0; r < px.world; r++) {
+        while (ld_acquire_sys_u64(flags + r) < e) {
+            if (clock64() - t0 > 40000000000ll) {  // ~20 s: a peer died; do not hang the GPU
+                c->peer_timeout = 1;
+                c->alive = 0;
+                return;
+            }
+            __nanosleep(100);
+        }
+    }
+    const unsigned par = (unsigned)(e & 1ull);
+    const double *slots = px.slots[px.rank];
+    double s = 0.0, a = 0.0;
+    for (int r = 0; r < px.world; r++) {
+        s += ld_relaxed_sys_f64(slots + ((size_t)par * px.world + r) * 2);
+        a += ld_relaxed_sys_f64(slots + ((size_t)par * px.world + r) * 2 + 1);
+    }
+    c->xchg += 1;
+    if (kind != TAIL_NONE) tail_logic(c, kind, s, a, it, last_in_iter, identity_res, 0, norm_log);
+}
+
 // CTA partial -> global partial array -> the last CTA to arrive sums all partials in index order.
 template <int NT>
 __device__ __forceinline__ void grid_reduce_and_tail(double sq, double aux, LoopCtl *ctl, double *partials, int kind,
@@ -222,7 +253,8 @@ __device__ __forceinline__ void grid_reduce_and_tail(double sq, double aux, Loop
                                                      double *norm_log, double *s_red, int *s_flag,
                                                      const PeerExchange *px = nullptr) {
     const bool p2p = px != nullptr && px->world > 1;
-    if (p2p) __threadfence_system();  // this thread's stores into peer memory, before the CTA reports in
+    // stores into peer memory: ordered by the CTA barriers inside block_sum + ONE cumulative system-scope fence by thread 0
+    // before the CTA reports in (a fence per thread — 9 000 MEMBAR.SYS per launch — is what round 1 paid here)
     double bs = block_sum<NT>(sq, s_red);
     double ba = identity_res ? block_sum<NT>(aux, s_red) : 0.0;
     if (threadIdx.x == 0) {
@@ -245,7 +277,8 @@ __device__ __forceinline__ void grid_reduce_and_tail(double sq, double aux, Loop
             ctl->ticket = 0;
             if (p2p) {
                 __threadfence_system();
-                peer_signal(ctl, *px, s, a);  // the wait kernel that follows runs tail_logic on the global sums
+                peer_signal(ctl, *px, s, a);
+                peer_consume(ctl, *px, kind, it, last_in_iter, identity_res, norm_log);  // global sums -> loop logic
             } else {
                 tail_logic(ctl, kind, s, a, it, last_in_iter, identity_res, defer, norm_log);
             }

@@ -223,12 +223,6 @@ PeerExchange make_px(const sb200_comm *c, int t_which, bool publish_x) {
     return px;
 }
 
-int32_t peer_wait(sb200_comm *c, LoopCtl *ctl, int kind, uint64_t it, int last, int identity, int force, double *norm_log,
-                  cudaStream_t st) {
-    return launch_peer_wait(ctl, c->arena.flags(c->rank), c->arena.slots(c->rank), c->world, c->epoch_base, kind,
-                            (uint32_t)it, last, identity, force, norm_log, st);
-}
-
 // The P2P flavour of sb200_dist_push_iterations_dev / sb200_dist_solve: same control flow as the NCCL flavour below,
 // the exchange is fused into the kernels (see PeerExchange in common.hpp).
 int32_t push_iterations_p2p(sb200_comm *c, sb200_matrix *mm, const DistPlan &p, Workspace &ws, const double *b_local_dev,
@@ -251,9 +245,9 @@ int32_t push_iterations_p2p(sb200_comm *c, sb200_matrix *mm, const DistPlan &p, 
     ia.ctl = ws.ctl.p;
     ia.partials = ws.partials.p;
     ia.row_base = (uint32_t)p.row0;
+    ia.norm_log = ws.norm_log.p;
     ia.px = make_px(c, 0, false);
     SB_TRY(launch_init_state(ia, st));
-    SB_TRY(peer_wait(c, ws.ctl.p, 1, 0, 0, 0, 1, ws.norm_log.p, st));
     TileKernelArgs base{};
     fill_tile_args(mm, base);
     base.ctl = ws.ctl.p;
@@ -262,6 +256,7 @@ int32_t push_iterations_p2p(sb200_comm *c, sb200_matrix *mm, const DistPlan &p, 
     base.force = 1;
     base.sol = x;
     base.dinv = mm->d_dinv[0].p;
+    base.norm_log = ws.norm_log.p;
     SB_CUDA(cudaEventRecord(ws.ev0, st));
     for (uint64_t it = 1; it <= nterms; it++) {
         TileKernelArgs a = base;
@@ -273,7 +268,6 @@ int32_t push_iterations_p2p(sb200_comm *c, sb200_matrix *mm, const DistPlan &p, 
         if (getenv("SUBLINEAR_B200_DEBUG_NOSTORE"))  // timing aid: compute + signalling only, no remote term stores
             for (int q = 0; q < c->world; q++) a.px.t_out[q] = nullptr;
         SB_TRY(launch_tile_kernel(cfg, EPI_PUSH, a, st));
-        SB_TRY(peer_wait(c, ws.ctl.p, 1, it, 0, 0, 1, ws.norm_log.p, st));
     }
     SB_CUDA(cudaEventRecord(ws.ev1, st));
     return SB200_OK;
@@ -567,7 +561,6 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
                 for (int q = 0; q < c->world; q++) dst[q] = c->arena.vec(q, 2);
                 SB_TRY(launch_peer_publish(ws->x.p, p.nloc, p.row0, dst, ws->ctl.p, make_px(c, -1, false), force, st));
                 launches++;
-                SB_TRY(peer_wait(c, ws->ctl.p, 0, it, 0, 0, force, nullptr, st));
             }
             xfull = c->arena.vec(c->rank, 2);
         } else if (multi) {
@@ -586,9 +579,7 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
         if (p2p) a.px = make_px(c, -1, false);
         launches++;
         SB_TRY(launch_tile_kernel(cfg, EPI_RESID, a, st));
-        if (p2p) {
-            SB_TRY(peer_wait(c, ws->ctl.p, 2, it, last, 0, force, nullptr, st));
-        } else if (multi) {
+        if (!p2p && multi) {
             SB_NCCL(g_nccl.AllReduce(ws->ctl.p->red, ws->ctl.p->red, 1, ncclDouble, ncclSum, c->comm, st));
             SB_TRY(launch_dist_tail(ws->ctl.p, 2, (uint32_t)it, last, 0, force, nullptr, st));
         }
@@ -625,7 +616,6 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
             double *dst[kMaxPeers];
             for (int q = 0; q < c->world; q++) dst[q] = c->arena.vec(q, 1);
             SB_TRY(launch_peer_publish(x0.p, p.nloc, p.row0, dst, ws->ctl.p, make_px(c, -1, false), 1, st));
-            SB_TRY(peer_wait(c, ws->ctl.p, 0, 0, 0, 0, 1, nullptr, st));
             x0full = T[1];
         } else if (multi) {
             SB_CUDA(cudaMemcpyAsync(T[1] + p.row0, x0.p, p.nloc * 8, cudaMemcpyDeviceToDevice, st));
@@ -664,9 +654,7 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
         if (p2p) ia.px = make_px(c, 0, resid_due);
         SB_TRY(launch_init_state(ia, st));
         launches++;
-        if (p2p) {
-            SB_TRY(peer_wait(c, ws->ctl.p, 1, 0, !resid_due, identity, 0, nullptr, st));
-        } else {
+        if (!p2p) {
             SB_TRY(exchange_term(c, ws->ctl.p, T[0], p.per, st));
             if (multi) SB_TRY(launch_dist_tail(ws->ctl.p, 1, 0, !resid_due, identity, 0, nullptr, st));
         }
@@ -699,9 +687,7 @@ int32_t sb200_dist_solve(sb200_comm *c, const sb200_solver *s, const sb200_matri
             SB_TRY(launch_tile_kernel(cfg, EPI_PUSH, a, st));
             if (profiling) SB_CUDA(cudaEventRecord(prof.back().e1, st));
             launches++;
-            if (p2p) {
-                SB_TRY(peer_wait(c, ws->ctl.p, 1, it, !resid_due, identity, 0, nullptr, st));
-            } else {
+            if (!p2p) {
                 SB_TRY(exchange_term(c, ws->ctl.p, T[it & 1], p.per, st));
                 if (multi) SB_TRY(launch_dist_tail(ws->ctl.p, 1, (uint32_t)it, !resid_due, identity, 0, nullptr, st));
             }

@@ -117,6 +117,7 @@ int32_t sb200_solve_entry(const sb200_matrix *m, const double *b, uint64_t blen,
         return fail(SB200_ERR_DIMENSION_MISMATCH, "Vector length %llu does not match matrix rows %llu",
                     (unsigned long long)blen, (unsigned long long)m->nrows);
     if (nqueries && (!rows || !est)) return fail(SB200_ERR_INVALID_INPUT, "null query or output array");
+    if (blen && !b) return fail(SB200_ERR_INVALID_INPUT, "b is null");
     if (nwalks == 0) {
         if (!(eps > 0.0)) return fail(SB200_ERR_INVALID_INPUT, "epsilon must be positive");  // validatePositiveNumber (:583)
         nwalks = (uint64_t)std::fmax(100.0, std::ceil(1.0 / (eps * eps)));  // :587

@@ -312,17 +312,19 @@ __device__ __forceinline__ void grid_reduce_and_tail_regs(double sq, double aux,
     const bool p2p = px != nullptr && px->world > 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned nparts = gridDim.x * WARPS;
-    if (p2p) __threadfence_system();  // this thread's stores into peer memory, before the CTA reports in
     sq = warp_sum(sq);
     if (identity_res) aux = warp_sum(aux);
     if (lane == 0) {
         partials[blockIdx.x * WARPS + warp] = sq;
         if (identity_res) partials[nparts + blockIdx.x * WARPS + warp] = aux;
-        if (p2p) __threadfence_system(); else __threadfence();
     }
     __syncthreads();
     int last = 0;
-    if (threadIdx.x == 0) last = atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        // one cumulative fence after the CTA barrier orders every thread's stores (partials, peer memory) before the ticket
+        if (p2p) __threadfence_system(); else __threadfence();
+        last = atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1;
+    }
     last = __syncthreads_or(last);
     if (last && warp == 0) {
         __threadfence();
@@ -336,7 +338,8 @@ __device__ __forceinline__ void grid_reduce_and_tail_regs(double sq, double aux,
             ctl->ticket = 0;
             if (p2p) {
                 __threadfence_system();
-                peer_signal(ctl, *px, s, a2);  // the wait kernel that follows runs tail_logic on the global sums
+                peer_signal(ctl, *px, s, a2);
+                peer_consume(ctl, *px, kind, it, last_in_iter, identity_res, norm_log);  // global sums -> loop logic
             } else {
                 tail_logic(ctl, kind, s, a2, it, last_in_iter, identity_res, defer, norm_log);
             }

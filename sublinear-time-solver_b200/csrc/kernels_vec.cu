@@ -128,52 +128,6 @@ int32_t launch_dist_tail(LoopCtl *ctl, int kind, uint32_t it, int last_in_iter, 
     return SB200_OK;
 }
 
-// P2P exchange, consumer side: one warp. Lane r waits for rank r's flag of the current exchange; lane 0 then adds the
-// ranks' partial sums in rank order (every rank computes the same bits) and runs the loop logic on them.
-__global__ void peer_wait_kernel(LoopCtl *c, const unsigned long long *flags, const double *slots, int world,
-                                 unsigned long long epoch_base, int kind, uint32_t it, int last_in_iter, int identity_res,
-                                 int force, double *norm_log) {
-    if (c->alive == 0 && !force) return;  // dead loop: nobody signalled, nothing to wait for
-    const unsigned long long e = epoch_base + c->xchg + 1ull;
-    const int lane = threadIdx.x;
-    bool ok = true;
-    if (lane < world) {
-        const long long t0 = clock64();
-        while (ld_acquire_sys_u64(flags + lane) < e) {
-            if (clock64() - t0 > 40000000000ll) {  // ~20 s: a peer died; do not hang the GPU
-                ok = false;
-                break;
-            }
-            __nanosleep(200);
-        }
-    }
-    ok = __all_sync(0xffffffffu, ok);
-    if (lane == 0) {
-        if (!ok) {
-            c->peer_timeout = 1;
-            c->alive = 0;
-            return;
-        }
-        const unsigned par = (unsigned)(e & 1ull);
-        double s = 0.0, a = 0.0;
-        for (int r = 0; r < world; r++) {
-            s += ld_relaxed_sys_f64(slots + ((size_t)par * world + r) * 2);
-            a += ld_relaxed_sys_f64(slots + ((size_t)par * world + r) * 2 + 1);
-        }
-        c->xchg += 1;
-        if (kind != TAIL_NONE) tail_logic(c, kind, s, a, it, last_in_iter, identity_res, 0, norm_log);
-    }
-}
-
-int32_t launch_peer_wait(LoopCtl *ctl, const unsigned long long *flags_local, const double *slots_local, int world,
-                         unsigned long long epoch_base, int kind, uint32_t it, int last_in_iter, int identity_res,
-                         int force, double *norm_log, cudaStream_t stream) {
-    peer_wait_kernel<<<1, 32, 0, stream>>>(ctl, flags_local, slots_local, world, epoch_base, kind, it, last_in_iter,
-                                          identity_res, force, norm_log);
-    SB_CUDA(cudaGetLastError());
-    return SB200_OK;
-}
-
 // P2P exchange, plain publish: src[0..n) -> dst_p[offset .. offset+n) on every rank, then signal (no sums).
 struct PublishDst {
     double *p[kMaxPeers];
@@ -186,16 +140,16 @@ __global__ void __launch_bounds__(256) peer_publish_kernel(const double *__restr
         const double v = src[i];
         for (int p = 0; p < px.world; p++) dst.p[p][offset + i] = v;
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        __threadfence_system();  // cumulative: after the barrier it orders the whole CTA's peer stores before the ticket
         unsigned t = atomicAdd(&ctl->ticket, 1u);
         s_flag = (t == gridDim.x - 1);
         if (s_flag) {
             ctl->ticket = 0;
             __threadfence_system();
             peer_signal(ctl, px, 0.0, 0.0);
+            peer_consume(ctl, px, TAIL_NONE, 0u, 0, 0, nullptr);
         }
     }
 }

@@ -181,9 +181,11 @@ static int32_t build_long_rows(sb200_matrix *m) {
 // vector and walking slab after slab keeps the gathers at one operation each; rows are column-sorted, so carrying the
 // row sum from slab to slab adds the products in exactly the CSR order.
 // $SUBLINEAR_B200_SLABS = 0 forbids, 2..8 forces that many slabs. Default: the gathered vector is > 48 MB and <= 8 * 28 MB
-// and the matrix holds enough entries per vector sector for the window to pay (a row block of the multi-GPU path gathers
-// from the full-length vector with only its share of the entries: $SUBLINEAR_B200_SLAB_MIN_DENSITY entries per 32-byte
-// sector of the vector, default 2). Needs every row sorted by column (checked on the device), otherwise the split is dropped.
+// and the matrix holds enough entries per vector sector for the window to pay: $SUBLINEAR_B200_SLAB_MIN_DENSITY entries
+// per 32-byte sector of the vector, default 8. A row block of the multi-GPU path gathers from the full-length vector with
+// only its share of the entries, and the slab walk produces its outputs (and with them the remote stores of the
+// exchange) only in the last slab phase: measured at 8 GPUs (profiles/r2_multi_gpu.md), 5 entries per sector, 202 us per
+// iteration with slabs vs 173 us single-pass although the slab kernel alone is the faster one (119 vs 146 us). Needs every row sorted by column (checked on the device), otherwise the split is dropped.
 static int32_t build_slabs(sb200_matrix *m) {
     m->nslabs = 0;
     if (m->tile_cfg >= 0 || m->nrows == 0 || m->nnz == 0) return SB200_OK;
@@ -198,7 +200,7 @@ static int32_t build_slabs(sb200_matrix *m) {
     } else {
         if (vec_bytes <= 48e6 || vec_bytes > kMaxSlabs * 28e6) return SB200_OK;
         const char *d = getenv("SUBLINEAR_B200_SLAB_MIN_DENSITY");
-        const double min_density = d ? atof(d) : 2.0;
+        const double min_density = d ? atof(d) : 8.0;
         if ((double)m->nnz < min_density * vec_bytes / 32.0) return SB200_OK;
         S = (int)std::ceil(vec_bytes / 28e6);
         if (S > kMaxSlabs) S = kMaxSlabs;

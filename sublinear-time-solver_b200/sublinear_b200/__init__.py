@@ -572,7 +572,8 @@ class NeumannSolver:
         """`solve` with `SolverOptions::streaming(interval)`: `callback(partial: dict) -> bool | None` receives a
         PartialSolution (src/solver/mod.rs:198-217) every `streaming_interval` iterations; return True to stop."""
         b = _f64(b)
-        o = options._c()
+        guess = None if options.initial_guess is None else _f64(options.initial_guess)
+        o = options._c(None if guess is None else guess.ctypes.data, 0 if guess is None else len(guess))
 
         def _cb(pp, _user):
             p = pp.contents
@@ -947,7 +948,8 @@ class Comm:
         options = options or SolverOptions()
         b = _f64(b_local)
         x = np.zeros(len(b))
-        o = options._c()
+        guess = None if options.initial_guess is None else _f64(options.initial_guess)   # this rank's rows of the guess
+        o = options._c(None if guess is None else guess.ctypes.data, 0 if guess is None else len(guess))
         r = _Result()
         rc = lib().sb200_dist_solve(self._h, solver._h, m_local._h, _ptr(b), len(b), C.byref(o), _ptr(x), C.byref(r))
         res = SolverResult._from(r, x)
