@@ -187,6 +187,9 @@ __device__ __forceinline__ void tail_logic(LoopCtl *c, int kind, double sum, dou
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -211,8 +214,10 @@ __device__ __forceinline__ void peer_signal(const LoopCtl *ctl, const PeerExchan
         st_relaxed_sys_f64(s, sum);
         st_relaxed_sys_f64(s + 1, aux);
     }
+    // release = ONE system-scope fence, then relaxed flag stores (a st.release per peer pays a fence + NVLink round trip
+    // each, serialised on the critical path of every exchange)
     __threadfence_system();
-    for (int p = 0; p < px.world; p++) st_release_sys_u64(px.flags[p] + px.rank, e);
+    for (int p = 0; p < px.world; p++) st_relaxed_sys_u64(px.flags[p] + px.rank, e);
 }
 
 // P2P consume, run by the thread that just signalled (the last CTA of a kernel): wait until every rank has raised its flag

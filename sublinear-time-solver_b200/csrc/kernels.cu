@@ -110,7 +110,7 @@ int tile_kernel_max_grid(int cfg, Epilogue epi) {
     if (launch_warp_any(epi, dummy, nullptr, &mg) != SB200_OK) return 0;
     if (launch_sell_any(epi, dummy, nullptr, &ms) != SB200_OK) return 0;  // one partial per warp
     if (launch_slab_kernel(epi, dummy, nullptr, &mf) != SB200_OK) return 0;
-    return std::max(mg, std::max(ms, mf));
+    return std::max(mg, std::max(ms, mf)) + 16;  // + scratch of the SELL kernel's last-CTA reduction (2 * 8 doubles)
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -303,7 +303,7 @@ static int32_t launch_warp_any(Epilogue epi, const TileKernelArgs &a, cudaStream
 //     the last CTA (elected with __syncthreads_or, no shared flag).
 // Padding slots hold value 0 / column 0 and are never gathered or added (k < row length), so non-finite x entries
 // cannot leak into other rows.
-// warp partial -> global partial array -> warp 0 of the last CTA sums all partials in index order. No shared memory.
+// warp partial -> global partial array -> the last CTA sums all partials in a fixed order. No shared memory.
 template <int NT>
 __device__ __forceinline__ void grid_reduce_and_tail_regs(double sq, double aux, LoopCtl *ctl, double *partials, int kind,
                                                           uint32_t it, int last_in_iter, int identity_res, int defer,
@@ -326,15 +326,40 @@ __device__ __forceinline__ void grid_reduce_and_tail_regs(double sq, double aux,
         last = atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1;
     }
     last = __syncthreads_or(last);
-    if (last && warp == 0) {
+    if (last) {
+        // the whole last CTA adds the partials (fixed order for a given grid: thread t takes t, t + NT, ... on four
+        // independent accumulators — one warp walking 9 000 partials with a dependent add per L2 round trip cost ~10 us per
+        // launch), then the warps' sums go through 2 * WARPS doubles of global scratch behind the partial arrays
         __threadfence();
-        double s = 0.0, a2 = 0.0;
-        for (unsigned i = lane; i < nparts; i += 32) s += __ldcg(partials + i);
-        if (identity_res)
-            for (unsigned i = lane; i < nparts; i += 32) a2 += __ldcg(partials + nparts + i);
-        s = warp_sum(s);
-        if (identity_res) a2 = warp_sum(a2);
+        double s4[4] = {0.0, 0.0, 0.0, 0.0}, a4[4] = {0.0, 0.0, 0.0, 0.0};
+        unsigned i = threadIdx.x;
+        for (; i + 3u * NT < nparts; i += 4u * NT) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) s4[q] += __ldcg(partials + i + q * NT);
+            if (identity_res) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) a4[q] += __ldcg(partials + nparts + i + q * NT);
+            }
+        }
+        for (; i < nparts; i += NT) {
+            s4[0] += __ldcg(partials + i);
+            if (identity_res) a4[0] += __ldcg(partials + nparts + i);
+        }
+        double s = warp_sum((s4[0] + s4[1]) + (s4[2] + s4[3]));
+        double a2 = identity_res ? warp_sum((a4[0] + a4[1]) + (a4[2] + a4[3])) : 0.0;
+        double *scratch = partials + 2u * nparts;
         if (lane == 0) {
+            __stcg(scratch + warp, s);
+            __stcg(scratch + WARPS + warp, a2);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s = 0.0;
+            a2 = 0.0;
+            for (int w = 0; w < WARPS; w++) {
+                s += __ldcg(scratch + w);
+                a2 += __ldcg(scratch + WARPS + w);
+            }
             ctl->ticket = 0;
             if (p2p) {
                 __threadfence_system();
