@@ -210,10 +210,10 @@ int32_t launch_setup_rows(const double *vals, const uint32_t *cols, const uint32
                           uint32_t row_base, int compat_diag, SetupOut out, cudaStream_t stream);
 // column-slab split at ingest (warp per 32-row block): per (row, slab) the u16 offset of the row's first entry inside its
 // block (bit 15 = hub row, left to the pre-pass) and per (block, slab) the u32 entry count; flags[0] receives 1 if some row is not sorted by column (then the split would change the
-// accumulation order and is not used), flags[1] the number of rows whose entries fall into more than one slab. After the
+// accumulation order and is not used), flags[1] the number of entries in rows that reach into more than one slab. After the
 // prefix sums over blk (per slab, plus the slab's base), the ordered fill.
 int32_t launch_slab_count(const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows, uint32_t slab_width, int nslabs,
-                          uint32_t long_row, uint16_t *rel, uint64_t rel_stride, uint32_t *blk, int *flags,
+                          uint32_t long_row, uint16_t *rel, uint64_t rel_stride, uint32_t *blk, unsigned long long *flags,
                           cudaStream_t stream);
 int32_t launch_slab_fill(const double *vals, const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows,
                          uint32_t slab_width, int nslabs, const uint16_t *rel, uint64_t rel_stride, const uint32_t *blk,

@@ -45,7 +45,7 @@ int32_t launch_csr_to_sell(const double *vals, const uint32_t *cols, const uint3
 __global__ void __launch_bounds__(256) slab_count_kernel(const uint32_t *__restrict__ cols, const uint32_t *__restrict__ row_ptr,
                                                          uint32_t nrows, uint32_t slab_width, int nslabs, uint32_t long_row,
                                                          uint16_t *__restrict__ rel, uint64_t rel_stride,
-                                                         uint32_t *__restrict__ blk, int *flags) {
+                                                         uint32_t *__restrict__ blk, unsigned long long *flags) {
     const int lane = threadIdx.x & 31;
     const uint32_t nblocks = (nrows + 31u) >> 5, nb1 = nblocks + 1u;
     const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(256) slab_count_kernel(const uint32_t *__restr
             int used = 0;
 #pragma unroll
             for (int s = 0; s < kMaxSlabs; s++) used += cnt[s] != 0u;
-            if (bad) flags[0] = 1;
-            if (used > 1) atomicAdd(flags + 1, 1);  // rows whose gathers spread over several slabs
+            if (bad) flags[0] = 1ull;
+            if (used > 1) atomicAdd(flags + 1, (unsigned long long)(re - rs));  // entries of rows that reach into several slabs
         }
 #pragma unroll
         for (int s = 0; s < kMaxSlabs; s++) {
@@ -136,7 +136,7 @@ static unsigned block_grid(uint32_t nrows) {
 }
 
 int32_t launch_slab_count(const uint32_t *cols, const uint32_t *row_ptr, uint32_t nrows, uint32_t slab_width, int nslabs,
-                          uint32_t long_row, uint16_t *rel, uint64_t rel_stride, uint32_t *blk, int *flags,
+                          uint32_t long_row, uint16_t *rel, uint64_t rel_stride, uint32_t *blk, unsigned long long *flags,
                           cudaStream_t stream) {
     slab_count_kernel<<<block_grid(nrows), 256, 0, stream>>>(cols, row_ptr, nrows, slab_width, nslabs, long_row, rel,
                                                              rel_stride, blk, flags);
