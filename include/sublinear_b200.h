@@ -352,9 +352,9 @@ typedef struct sb200_push_graph sb200_push_graph;
 typedef struct sb200_push_config {
     double alpha;               /* 0.15 restart probability */
     double epsilon;             /* 1e-6: a node is pushed while residual >= epsilon * max(degree, 1) */
-    uint64_t max_pushes;        /* 1 000 000; checked between rounds here (the last round may overshoot) */
-    double queue_threshold;     /* 1e-8: admission test residual / max(degree, 1) >= threshold, applied when not adaptive */
-    int32_t adaptive_threshold; /* 1: the reference decays the threshold while its queue is short; modelled as 0 */
+    uint64_t max_pushes;        /* 1 000 000; never exceeded (the round that reaches it pushes the lowest node ids only) */
+    double queue_threshold;     /* 1e-8: admission test residual / max(degree, 1) >= threshold */
+    int32_t adaptive_threshold; /* 1: threshold x1.1 / x0.9 every 1 000 pushes by queue length (src/graph/mod.rs:204-212) */
     int32_t reserved;
 } sb200_push_config;
 /* ForwardPushResult / BackwardPushResult (forward_push.rs:10-22) minus the two vectors (caller buffers). */
@@ -363,9 +363,11 @@ typedef struct sb200_push_stats {
     uint64_t nodes_visited;
     double residual_norm;       /* L2 norm of the residual vector (forward_push.rs:217-219) */
     /* extensions */
-    uint64_t rounds;            /* frontier-synchronous rounds (every node above its threshold is pushed at once) */
+    uint64_t rounds;            /* rounds: every queued node above its threshold is pushed in the same round */
     uint64_t kernel_launches;
     double device_time_ms;
+    uint64_t dense_rounds;      /* rounds run as select + SpMV over the whole graph (frontier above nnz / 4 edges) */
+    uint64_t edges_touched;     /* edges read by the pushes: the work of the walk (nnz per dense round) */
 } sb200_push_stats;
 void sb200_push_config_default(sb200_push_config *c);
 /* PushGraph::from_matrix(&CompressedSparseRow) (adjacency.rs:211-224): row u = out-edges of u, weights >= 0. */
@@ -379,16 +381,52 @@ int32_t sb200_push_graph_degrees(const sb200_push_graph *g, uint64_t node, doubl
 void sb200_push_graph_free(sb200_push_graph *g);
 /* ForwardPushSolver::solve_single_source (nsources = 1: unit mass; an out-of-range source gives the all-zero result) /
  * solve_multi_source (mass 1/nsources per listed source) (forward_push.rs:66-177). estimate / residual: n doubles each.
- * The reference pushes one node at a time in priority order (its queue item has no Ord impl: the order is undefined);
- * here every node above its threshold is pushed in the same round (deterministic, no atomics). Same push rule, same
- * stopping condition, same invariants: estimate, residual >= 0, sum(estimate) + sum(residual) = 1 for the forward
- * direction, residual < epsilon * max(degree, 1) everywhere at exit. */
+ * The reference pushes one node at a time in priority order; here every queued node above its threshold is pushed in
+ * the same round and only the frontier's edges are read (sparse frontier: candidate list -> flag / scan -> expand ->
+ * stable sort by neighbour -> ordered reduce; deterministic, no floating-point atomics). Same push rule, same stopping
+ * condition, same invariants: estimate, residual >= 0, sum(estimate) + sum(residual) = 1 for the forward direction,
+ * residual < epsilon * max(degree, 1) everywhere at exit. */
 int32_t sb200_forward_push(const sb200_push_graph *g, const sb200_push_config *cfg, const uint64_t *sources,
                            uint64_t nsources, double *estimate, double *residual, sb200_push_stats *stats);
 /* BackwardPushSolver::solve_single_target / solve_multi_target (backward_push.rs:66-220): mass moves to the
  * predecessors with weight / max(out_degree(predecessor), 1); thresholds use the in-degree. */
 int32_t sb200_backward_push(const sb200_push_graph *g, const sb200_push_config *cfg, const uint64_t *targets,
                             uint64_t ntargets, double *estimate, double *residual, sb200_push_stats *stats);
+/* ForwardPushSolver::solve_with_target (forward_push.rs:234-290): stops once estimate[target] > target_precision and
+ * residual[target] < 0.1 target_precision (tested once per round here, before every pop in the reference). */
+int32_t sb200_forward_push_with_target(const sb200_push_graph *g, const sb200_push_config *cfg, uint64_t source,
+                                       uint64_t target, double target_precision, double *estimate, double *residual,
+                                       sb200_push_stats *stats);
+/* BackwardPushSolver::solve_with_source (backward_push.rs:238-290). */
+int32_t sb200_backward_push_with_source(const sb200_push_graph *g, const sb200_push_config *cfg, uint64_t source,
+                                        uint64_t target, double source_precision, double *estimate, double *residual,
+                                        sb200_push_stats *stats);
+/* BackwardPushSolver::combine_with_forward (backward_push.rs:312-330). */
+int32_t sb200_push_combine_with_forward(double alpha, const double *backward_estimate, const double *backward_residual,
+                                        uint64_t nbackward, const double *forward_estimate, const double *forward_residual,
+                                        uint64_t nforward, double *out);
+/* BidirectionalPushSolver::solve_bidirectional / adaptive_solve (backward_push.rs:362-420). */
+int32_t sb200_bidirectional_push(const sb200_push_graph *g, const sb200_push_config *forward_cfg,
+                                 const sb200_push_config *backward_cfg, uint64_t source, uint64_t target, double *out);
+int32_t sb200_bidirectional_adaptive_push(const sb200_push_graph *g, const sb200_push_config *forward_cfg,
+                                          const sb200_push_config *backward_cfg, uint64_t source, uint64_t target, double *out);
+
+/* SublinearSolver.solveForwardPush (src/core/solver.ts:437-522) for A x = b: the residual r = b - A x is kept exact, a push
+ * of node i sets x_i += r_i / a_ii, r_i = 0, r_j -= a_ji r_i / a_ii down column i. The reference pushes the node of largest
+ * |r| per iteration; here every queued node with |r_i| >= epsilon is pushed per round (sparse frontier, as above).
+ * Converged: max |r| < epsilon. `iterations` counts node pushes; reaching max_iterations without convergence returns
+ * SB200_ERR_CONVERGENCE_FAILURE, a zero diagonal under a pushed node SB200_ERR_NUMERICAL_INSTABILITY (x_out and stats
+ * are filled in both cases). */
+typedef struct sb200_axb_push_stats {
+    uint64_t iterations;
+    uint64_t rounds;
+    double residual_norm;       /* ||b - A x||_2 (VectorOperations.norm2(residual)) */
+    double max_residual;        /* max |r_i| */
+    int32_t converged;
+    int32_t reserved;
+} sb200_axb_push_stats;
+int32_t sb200_forward_push_solve(const sb200_matrix *m, const double *b, uint64_t blen, double epsilon,
+                                 uint64_t max_iterations, double *x_out, sb200_axb_push_stats *stats);
 
 /* ---------------------------------------------------------------------------------------------- */
 /* single-entry estimation and PageRank (TS-only front doors)               */

@@ -132,6 +132,13 @@ def lib(fast: bool = False, out_dir: str | None = None):
     L.orc_push_config_default.restype = None
     for f in (L.orc_forward_push, L.orc_backward_push):
         f.argtypes = [C.POINTER(_Csr), C.POINTER(_PushConfig), u64p, C.c_uint64, f64p, f64p, C.POINTER(_PushStats)]
+    for f in (L.orc_forward_push_with_target, L.orc_backward_push_with_source):
+        f.argtypes = [C.POINTER(_Csr), C.POINTER(_PushConfig), C.c_uint64, C.c_uint64, C.c_double, f64p, f64p,
+                      C.POINTER(_PushStats)]
+    L.orc_push_combine_with_forward.argtypes = [C.c_double, f64p, f64p, C.c_uint64, f64p, f64p, C.c_uint64]
+    L.orc_push_combine_with_forward.restype = C.c_double
+    L.orc_ts_forward_push.argtypes = [C.POINTER(_Csr), f64p, C.c_uint64, C.c_double, C.c_uint64, f64p, u64p, f64p,
+                                      C.POINTER(C.c_int)]
     L.orc_cg_solve.argtypes = [C.POINTER(_Csr), f64p, C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_int,
                                C.POINTER(_CgResult)]
     L.orc_gen_bench_k.argtypes = [C.c_uint64, C.c_double]
@@ -392,6 +399,66 @@ def backward_push(adj: Csr, targets, alpha=0.15, epsilon=1e-6, max_pushes=1_000_
                   adaptive_threshold=True) -> PushResult:
     """BackwardPushSolver::solve_single_target / solve_multi_target (src/solver/backward_push.rs:66-177) restated."""
     return _push("orc_backward_push", adj, targets, alpha, epsilon, max_pushes, queue_threshold, adaptive_threshold)
+
+
+def _push_watch(fn_name, adj: Csr, source, target, precision, alpha, epsilon, max_pushes, queue_threshold,
+                adaptive_threshold):
+    L = lib()
+    c = _PushConfig()
+    L.orc_push_config_default(C.byref(c))
+    c.alpha, c.epsilon, c.max_pushes = alpha, epsilon, max_pushes
+    c.queue_threshold, c.adaptive_threshold = queue_threshold, int(adaptive_threshold)
+    est, res = np.zeros(adj.nrows), np.zeros(adj.nrows)
+    st = _PushStats()
+    a = adj.c()
+    rc = getattr(L, fn_name)(C.byref(a), C.byref(c), source, target, precision, _p(est, C.c_double), _p(res, C.c_double),
+                             C.byref(st))
+    if rc != OK:
+        raise OracleError(rc, fn_name)
+    return PushResult(est, res, int(st.push_count), int(st.nodes_visited), st.residual_norm)
+
+
+def forward_push_with_target(adj: Csr, source, target, target_precision, alpha=0.15, epsilon=1e-6, max_pushes=1_000_000,
+                             queue_threshold=1e-8, adaptive_threshold=True) -> PushResult:
+    """ForwardPushSolver::solve_with_target (src/solver/forward_push.rs:234-290) restated."""
+    return _push_watch("orc_forward_push_with_target", adj, source, target, target_precision, alpha, epsilon, max_pushes,
+                       queue_threshold, adaptive_threshold)
+
+
+def backward_push_with_source(adj: Csr, source, target, source_precision, alpha=0.15, epsilon=1e-6, max_pushes=1_000_000,
+                              queue_threshold=1e-8, adaptive_threshold=True) -> PushResult:
+    """BackwardPushSolver::solve_with_source (src/solver/backward_push.rs:238-290) restated."""
+    return _push_watch("orc_backward_push_with_source", adj, source, target, source_precision, alpha, epsilon, max_pushes,
+                       queue_threshold, adaptive_threshold)
+
+
+def push_combine_with_forward(alpha, backward: PushResult, forward_estimate, forward_residual) -> float:
+    """BackwardPushSolver::combine_with_forward (src/solver/backward_push.rs:312-330) restated."""
+    be, br, fe, fr = _f64(backward.estimate), _f64(backward.residual), _f64(forward_estimate), _f64(forward_residual)
+    return float(lib().orc_push_combine_with_forward(alpha, _p(be, C.c_double), _p(br, C.c_double), len(be),
+                                                     _p(fe, C.c_double), _p(fr, C.c_double), len(fe)))
+
+
+@dataclass
+class TsPushResult:
+    solution: np.ndarray
+    iterations: int
+    residual: float
+    converged: bool
+    status: int
+
+
+def ts_forward_push(a: Csr, b, epsilon=1e-6, max_iterations=1000) -> TsPushResult:
+    """SublinearSolver.solveForwardPush (src/core/solver.ts:437-522) restated (Gauss-Southwell, one node per iteration)."""
+    b = _f64(b)
+    x = np.zeros(a.nrows)
+    it, res, conv = C.c_uint64(), C.c_double(), C.c_int()
+    ac = a.c()
+    rc = lib().orc_ts_forward_push(C.byref(ac), _p(b, C.c_double), len(b), epsilon, max_iterations, _p(x, C.c_double),
+                                   C.byref(it), C.byref(res), C.byref(conv))
+    if rc not in (OK, ERR_CONVERGENCE_FAILURE, ERR_NUMERICAL_INSTABILITY):
+        raise OracleError(rc, "ts_forward_push")
+    return TsPushResult(x, int(it.value), res.value, bool(conv.value), rc)
 
 
 @dataclass

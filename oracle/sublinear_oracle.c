@@ -678,7 +678,8 @@ static void wq_adaptive(wqueue *q, uint64_t max_size, uint64_t min_size) { /* :2
 /* direction 0: forward (mass moves along out-edges, thresholds on the out-degree);
  * direction 1: backward (mass moves to predecessors with weight / max(out_degree(pred), 1), thresholds on the in-degree) */
 static int push_run(const orc_csr *adj, const orc_push_config *cfg, const uint64_t *seeds, uint64_t nseeds,
-                    int direction, double *est, double *res, orc_push_stats *stats) {
+                    int direction, int watch, uint64_t watch_node, double watch_precision, double *est, double *res,
+                    orc_push_stats *stats) {
     if (adj->nrows != adj->ncols) return ORC_ERR_INVALID_INPUT;
     uint64_t n = adj->nrows;
     double *deg = (double *)calloc(n ? n : 1, sizeof(double));   /* row sums (adjacency.rs:214) */
@@ -725,6 +726,8 @@ static int push_run(const orc_csr *adj, const orc_push_config *cfg, const uint64
             if (seeds[s] < n) wq_push_if_threshold(&q, seeds[s], res[seeds[s]], fmax(tdeg[seeds[s]], 1.0));
     uint64_t node;
     while (q.len > 0 && push_count < cfg->max_pushes) {
+        /* solve_with_target (forward_push.rs:260-263) / solve_with_source (backward_push.rs:263-266): before every pop */
+        if (watch && est[watch_node] > watch_precision && res[watch_node] < watch_precision * 0.1) break;
         if (!wq_pop(&q, &node)) break;
         if (res[node] < cfg->epsilon * fmax(tdeg[node], 1.0)) continue;
         /* push_node / backward_push_node */
@@ -767,12 +770,100 @@ static int push_run(const orc_csr *adj, const orc_push_config *cfg, const uint64
 
 int orc_forward_push(const orc_csr *adj, const orc_push_config *cfg, const uint64_t *sources, uint64_t nsources,
                      double *est, double *res, orc_push_stats *stats) {
-    return push_run(adj, cfg, sources, nsources, 0, est, res, stats);
+    return push_run(adj, cfg, sources, nsources, 0, 0, 0, 0.0, est, res, stats);
 }
 
 int orc_backward_push(const orc_csr *adj, const orc_push_config *cfg, const uint64_t *targets, uint64_t ntargets,
                       double *est, double *res, orc_push_stats *stats) {
-    return push_run(adj, cfg, targets, ntargets, 1, est, res, stats);
+    return push_run(adj, cfg, targets, ntargets, 1, 0, 0, 0.0, est, res, stats);
+}
+
+/* ForwardPushSolver::solve_with_target (forward_push.rs:234-290): out-of-range source or target -> all-zero result */
+int orc_forward_push_with_target(const orc_csr *adj, const orc_push_config *cfg, uint64_t source, uint64_t target,
+                                 double target_precision, double *est, double *res, orc_push_stats *stats) {
+    uint64_t seed = (source >= adj->nrows || target >= adj->nrows) ? adj->nrows : source;
+    return push_run(adj, cfg, &seed, 1, 0, seed < adj->nrows, target, target_precision, est, res, stats);
+}
+
+/* BackwardPushSolver::solve_with_source (backward_push.rs:238-290) */
+int orc_backward_push_with_source(const orc_csr *adj, const orc_push_config *cfg, uint64_t source, uint64_t target,
+                                  double source_precision, double *est, double *res, orc_push_stats *stats) {
+    uint64_t seed = (source >= adj->nrows || target >= adj->nrows) ? adj->nrows : target;
+    return push_run(adj, cfg, &seed, 1, 1, seed < adj->nrows, source, source_precision, est, res, stats);
+}
+
+/* BackwardPushSolver::combine_with_forward (backward_push.rs:312-330) */
+double orc_push_combine_with_forward(double alpha, const double *best, const double *bres, uint64_t nb, const double *fest,
+                                     const double *fres, uint64_t nf) {
+    double total = 0.0;
+    uint64_t m = nb < nf ? nb : nf;
+    for (uint64_t i = 0; i < m; i++) {
+        total += best[i] * fest[i];
+        total += bres[i] * fest[i] * alpha;
+        total += best[i] * fres[i] * alpha;
+    }
+    return total;
+}
+
+/* SublinearSolver.solveForwardPush (src/core/solver.ts:437-522): Gauss-Southwell push on the residual of A x = b.
+ * The column walk `for j != maxNode: residual[j] -= getEntry(j, maxNode) * pushValue` runs over the transposed copy
+ * (entries of column maxNode in ascending row order; duplicate entries are applied one after the other, getEntry's
+ * first-match rule differs only for duplicated coordinates, which this path does not produce).
+ * Returns ORC_OK, ORC_ERR_CONVERGENCE_FAILURE (maxIterations exhausted, :505-511) or ORC_ERR_NUMERICAL_INSTABILITY
+ * (|diagonal| < 1e-15 under the pushed node, :468-471). */
+int orc_ts_forward_push(const orc_csr *a, const double *b, uint64_t blen, double epsilon, uint64_t max_iterations,
+                        double *x, uint64_t *iterations, double *residual_norm, int *converged) {
+    if (a->nrows != a->ncols || blen != a->nrows) return ORC_ERR_DIMENSION_MISMATCH;
+    uint64_t n = a->nrows;
+    double *r = (double *)malloc((n ? n : 1) * sizeof(double));
+    double *diag = (double *)calloc(n ? n : 1, sizeof(double));
+    uint32_t *tptr = (uint32_t *)calloc(n + 1, sizeof(uint32_t));
+    uint32_t *trow = (uint32_t *)malloc((a->nnz ? a->nnz : 1) * sizeof(uint32_t));
+    double *tval = (double *)malloc((a->nnz ? a->nnz : 1) * sizeof(double));
+    for (uint64_t k = 0; k < a->nnz; k++) tptr[a->col_indices[k] + 1]++;
+    for (uint64_t i = 0; i < n; i++) tptr[i + 1] += tptr[i];
+    {
+        uint32_t *pos = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t));
+        memcpy(pos, tptr, n * sizeof(uint32_t));
+        for (uint64_t i = 0; i < n; i++)
+            for (uint64_t k = a->row_ptr[i]; k < a->row_ptr[i + 1]; k++) {
+                uint32_t c = a->col_indices[k];
+                trow[pos[c]] = (uint32_t)i;
+                tval[pos[c]] = a->values[k];
+                pos[c]++;
+                if (c == i) diag[i] += a->values[k];
+            }
+        free(pos);
+    }
+    for (uint64_t i = 0; i < n; i++) { x[i] = 0.0; r[i] = b[i]; }
+    int conv = 0, rc = ORC_OK;
+    uint64_t it = 0;
+    for (uint64_t iter = 0; iter < max_iterations; iter++) {
+        double max_res = 0.0;
+        int64_t max_node = -1;
+        for (uint64_t i = 0; i < n; i++)  /* first strict maximum of |residual| (:455-461) */
+            if (fabs(r[i]) > max_res) { max_res = fabs(r[i]); max_node = (int64_t)i; }
+        if (max_res < epsilon) { conv = 1; break; }
+        if (fabs(diag[max_node]) < 1e-15) { rc = ORC_ERR_NUMERICAL_INSTABILITY; break; }
+        double push = r[max_node] / diag[max_node];
+        x[max_node] += push;
+        r[max_node] = 0.0;
+        for (uint64_t k = tptr[max_node]; k < tptr[max_node + 1]; k++)
+            if (trow[k] != (uint64_t)max_node) r[trow[k]] -= tval[k] * push;
+        it = iter + 1;
+    }
+    if (!conv && rc == ORC_OK) {
+        /* the loop may also end exactly converged after the last allowed push: the reference only learns that at the top
+         * of the next iteration, which does not exist -> CONVERGENCE_FAILED (:505-511) */
+        rc = ORC_ERR_CONVERGENCE_FAILURE;
+    }
+    double nrm = 0.0;
+    for (uint64_t i = 0; i < n; i++) nrm += r[i] * r[i];
+    if (iterations) *iterations = it;
+    if (residual_norm) *residual_norm = sqrt(nrm);
+    if (converged) *converged = conv;
+    free(r); free(diag); free(tptr); free(trow); free(tval);
+    return rc;
 }
 
 /* ------------------------------------------------------------------------------------------ */

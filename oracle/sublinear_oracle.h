@@ -179,6 +179,17 @@ int orc_forward_push(const orc_csr *adj, const orc_push_config *cfg, const uint6
                      double *est, double *res, orc_push_stats *stats);
 int orc_backward_push(const orc_csr *adj, const orc_push_config *cfg, const uint64_t *targets, uint64_t ntargets,
                       double *est, double *res, orc_push_stats *stats);
+/* solve_with_target (forward_push.rs:234-290) / solve_with_source (backward_push.rs:238-290) / combine_with_forward
+ * (backward_push.rs:312-330) */
+int orc_forward_push_with_target(const orc_csr *adj, const orc_push_config *cfg, uint64_t source, uint64_t target,
+                                 double target_precision, double *est, double *res, orc_push_stats *stats);
+int orc_backward_push_with_source(const orc_csr *adj, const orc_push_config *cfg, uint64_t source, uint64_t target,
+                                  double source_precision, double *est, double *res, orc_push_stats *stats);
+double orc_push_combine_with_forward(double alpha, const double *best, const double *bres, uint64_t nb, const double *fest,
+                                     const double *fres, uint64_t nf);
+/* SublinearSolver.solveForwardPush (src/core/solver.ts:437-522) */
+int orc_ts_forward_push(const orc_csr *a, const double *b, uint64_t blen, double epsilon, uint64_t max_iterations,
+                        double *x, uint64_t *iterations, double *residual_norm, int *converged);
 
 /* ---- conjugate gradient on the same SpMV ----
  * OptimizedConjugateGradientSolver::solve (src/optimized_solver.rs:182-295); the same loop is

@@ -14,6 +14,7 @@ sb200_matrix::~sb200_matrix() {
     cudaGetDevice(&prev);
     cudaSetDevice(device);
     pool.clear();
+    if (axb_cache && axb_cache_free) axb_cache_free(axb_cache);
     d_vals.release();
     d_cols.release();
     d_row_ptr.release();

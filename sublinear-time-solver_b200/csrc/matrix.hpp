@@ -85,6 +85,10 @@ struct sb200_matrix {
 
     std::vector<std::unique_ptr<sb200::Workspace>> pool;
 
+    // columns of A + diagonal for the A x = b forward push (csrc/push.cu), built on first use
+    void *axb_cache = nullptr;
+    void (*axb_cache_free)(void *) = nullptr;
+
     ~sb200_matrix();
 };
 

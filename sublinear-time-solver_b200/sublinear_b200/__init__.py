@@ -75,7 +75,13 @@ class _PushConfig(C.Structure):
 
 class _PushStats(C.Structure):
     _fields_ = [("push_count", C.c_uint64), ("nodes_visited", C.c_uint64), ("residual_norm", C.c_double),
-                ("rounds", C.c_uint64), ("kernel_launches", C.c_uint64), ("device_time_ms", C.c_double)]
+                ("rounds", C.c_uint64), ("kernel_launches", C.c_uint64), ("device_time_ms", C.c_double),
+                ("dense_rounds", C.c_uint64), ("edges_touched", C.c_uint64)]
+
+
+class _AxbPushStats(C.Structure):
+    _fields_ = [("iterations", C.c_uint64), ("rounds", C.c_uint64), ("residual_norm", C.c_double),
+                ("max_residual", C.c_double), ("converged", C.c_int32), ("reserved", C.c_int32)]
 
 
 class _CgConfig(C.Structure):
@@ -190,6 +196,12 @@ def lib():
         "sb200_push_graph_free": ([vp], None),
         "sb200_forward_push": ([vp, P(_PushConfig), vp, u64, vp, vp, P(_PushStats)], i32),
         "sb200_backward_push": ([vp, P(_PushConfig), vp, u64, vp, vp, P(_PushStats)], i32),
+        "sb200_forward_push_with_target": ([vp, P(_PushConfig), u64, u64, f64, vp, vp, P(_PushStats)], i32),
+        "sb200_backward_push_with_source": ([vp, P(_PushConfig), u64, u64, f64, vp, vp, P(_PushStats)], i32),
+        "sb200_push_combine_with_forward": ([f64, vp, vp, u64, vp, vp, u64, P(f64)], i32),
+        "sb200_bidirectional_push": ([vp, P(_PushConfig), P(_PushConfig), u64, u64, P(f64)], i32),
+        "sb200_bidirectional_adaptive_push": ([vp, P(_PushConfig), P(_PushConfig), u64, u64, P(f64)], i32),
+        "sb200_forward_push_solve": ([vp, vp, u64, f64, u64, vp, P(_AxbPushStats)], i32),
         "sb200_cg_config_default": ([P(_CgConfig)], None),
         "sb200_cg_solve": ([vp, vp, u64, P(_CgConfig), P(_CgResult)], i32),
         "sb200_cg_solve_into": ([vp, vp, u64, P(_CgConfig), vp, P(_CgResult)], i32),
@@ -779,6 +791,8 @@ class PushResult:
     rounds: int
     kernel_launches: int
     device_time_ms: float
+    dense_rounds: int = 0
+    edges_touched: int = 0
 
 
 class PushGraph:
@@ -844,8 +858,20 @@ class _PushSolver:
         c = self.config._c()
         st = _PushStats()
         _check(getattr(lib(), self._fn)(self.graph._h, C.byref(c), _ptr(s), len(s), _ptr(est), _ptr(res), C.byref(st)))
+        return self._result(est, res, st)
+
+    @staticmethod
+    def _result(est, res, st) -> PushResult:
         return PushResult(est, res, int(st.push_count), int(st.nodes_visited), st.residual_norm, int(st.rounds),
-                          int(st.kernel_launches), st.device_time_ms)
+                          int(st.kernel_launches), st.device_time_ms, int(st.dense_rounds), int(st.edges_touched))
+
+    def _run_watch(self, fn, source, target, precision) -> PushResult:
+        n = self.graph.num_nodes()
+        est, res = np.zeros(n), np.zeros(n)
+        c = self.config._c()
+        st = _PushStats()
+        _check(getattr(lib(), fn)(self.graph._h, C.byref(c), source, target, precision, _ptr(est), _ptr(res), C.byref(st)))
+        return self._result(est, res, st)
 
 
 class ForwardPushSolver(_PushSolver):
@@ -861,6 +887,10 @@ class ForwardPushSolver(_PushSolver):
     def query_single_entry(self, source, target) -> float:
         r = self.solve_single_source(source)
         return float(r.estimate[target]) if target < len(r.estimate) else 0.0
+
+    def solve_with_target(self, source, target, target_precision) -> PushResult:
+        """`solve_with_target` (forward_push.rs:234-290): early stop once the target's estimate is settled"""
+        return self._run_watch("sb200_forward_push_with_target", source, target, target_precision)
 
     def extrapolated_solution(self, result: PushResult) -> np.ndarray:
         return result.estimate + self.config.alpha * result.residual
@@ -879,6 +909,69 @@ class BackwardPushSolver(_PushSolver):
     def query_transition_probability(self, source, target) -> float:
         r = self.solve_single_target(target)
         return float(r.estimate[source]) if source < len(r.estimate) else 0.0
+
+    def solve_with_source(self, source, target, source_precision) -> PushResult:
+        """`solve_with_source` (backward_push.rs:238-290)"""
+        return self._run_watch("sb200_backward_push_with_source", source, target, source_precision)
+
+    def reachability_probabilities(self, target) -> np.ndarray:
+        return self.extrapolated_solution(self.solve_single_target(target))
+
+    def extrapolated_solution(self, result: PushResult) -> np.ndarray:
+        return result.estimate + self.config.alpha * result.residual
+
+    def combine_with_forward(self, backward_result: PushResult, forward_estimate, forward_residual) -> float:
+        """`combine_with_forward` (backward_push.rs:312-330)"""
+        fe, fr = _f64(forward_estimate), _f64(forward_residual)
+        be, br = _f64(backward_result.estimate), _f64(backward_result.residual)
+        out = C.c_double()
+        _check(lib().sb200_push_combine_with_forward(self.config.alpha, _ptr(be), _ptr(br), len(be), _ptr(fe), _ptr(fr),
+                                                     len(fe), C.byref(out)))
+        return out.value
+
+
+class BidirectionalPushSolver:
+    """`BidirectionalPushSolver` (src/solver/backward_push.rs:338-420)."""
+
+    def __init__(self, graph: PushGraph, forward_config: PushConfig | None = None, backward_config: PushConfig | None = None):
+        self.graph = graph
+        self.forward_config, self.backward_config = forward_config or PushConfig(), backward_config or PushConfig()
+
+    def _call(self, fn, source, target) -> float:
+        fc, bc = self.forward_config._c(), self.backward_config._c()
+        out = C.c_double()
+        _check(getattr(lib(), fn)(self.graph._h, C.byref(fc), C.byref(bc), source, target, C.byref(out)))
+        return out.value
+
+    def solve_bidirectional(self, source, target) -> float:
+        return self._call("sb200_bidirectional_push", source, target)
+
+    def adaptive_solve(self, source, target) -> float:
+        return self._call("sb200_bidirectional_adaptive_push", source, target)
+
+
+@dataclass
+class ForwardPushSolveResult:
+    """result of the TS solver's `solveForwardPush` (src/core/solver.ts:513-521)"""
+    solution: np.ndarray
+    iterations: int
+    residual: float
+    converged: bool
+    rounds: int
+    max_residual: float
+    method: str = "forward-push"
+
+
+def forward_push_solve(matrix: "SparseMatrix", b, epsilon=1e-6, max_iterations=1000) -> ForwardPushSolveResult:
+    """`SublinearSolver.solveForwardPush` (src/core/solver.ts:437-522) for A x = b (defaults: SolverConfig of the TS
+    package). Raises SolverError ConvergenceFailure / NumericalInstability like the reference throws."""
+    b = _f64(b)
+    x = np.zeros(len(b))
+    st = _AxbPushStats()
+    rc = lib().sb200_forward_push_solve(matrix._h, _ptr(b), len(b), epsilon, max_iterations, _ptr(x), C.byref(st))
+    res = ForwardPushSolveResult(x, int(st.iterations), st.residual_norm, bool(st.converged), int(st.rounds), st.max_residual)
+    _check(rc, res)
+    return res
 
 
 def push_iterations_dev(matrix: SparseMatrix, b_ptr: int, n: int, nterms: int, x_ptr: int = 0, t_ptr: int = 0,

@@ -147,6 +147,33 @@ def test_initial_guess_state_and_cg_in_slab_layout(oracle, monkeypatch, layout):
     np.testing.assert_allclose(rc.solution, oc.solution, rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("layout", ["csr", "slabs2", "slabs3"])
+def test_hub_rows_in_every_layout(oracle, monkeypatch, layout):
+    """rows above 1024 entries (hub rows of power-law graphs) are summed by the grid-wide pre-pass (lane-strided order:
+    tolerance-level parity); the other rows of the same 32-row blocks must stay bit-exact, in the slab layout too (hub
+    rows are only marked there: bit 15 of their row offset)"""
+    O = oracle
+    set_layout(monkeypatch, layout)
+    rng = np.random.default_rng(17)
+    n = 40_000
+    hubs = np.array([3, 64, 65, 9000, 39_999])
+    rows = np.concatenate([np.repeat(hubs, [5000, 1500, 30_000, 1025, 2000]), rng.integers(0, n, 300_000)])
+    cols = rng.integers(0, n, len(rows))
+    vals = rng.standard_normal(len(rows))
+    A = O.Csr.from_triplets(rows, cols, vals, n, n)
+    m = to_gpu(A)
+    x = rng.standard_normal(n)
+    y, ref = m.multiply_vector(x), A.multiply_vector(x)
+    lens = np.diff(A.row_ptr.astype(np.int64))
+    short = lens <= 1024
+    assert (~short).sum() == len(hubs)
+    assert np.array_equal(y[short], ref[short])
+    np.testing.assert_allclose(y[~short], ref[~short], rtol=1e-11, atol=1e-11)
+    y0 = rng.standard_normal(n)
+    ya = m.multiply_vector_add(x, y0)
+    np.testing.assert_allclose(ya, y0 + ref, rtol=1e-11, atol=1e-10)
+
+
 def _sym(n, k):
     rng = np.random.default_rng(n + k)
     r = np.repeat(np.arange(n), k)
