@@ -96,9 +96,7 @@ __global__ void walk_finalize_kernel(const double *__restrict__ part, uint32_t n
     var[q] = nwalks > 1 ? (c - (double)nwalks * mean * mean) / (double)(nwalks - 1) : 0.0;
 }
 
-int32_t triplets_to_csr(const uint64_t *rows, const uint64_t *cols, const double *vals, uint64_t nt, uint64_t nrows,
-                        uint64_t ncols, int dup_policy, std::vector<uint64_t> &row_ptr, std::vector<uint32_t> &ci,
-                        std::vector<double> &cv);
+
 
 }  // namespace sb200
 
@@ -163,52 +161,6 @@ int32_t sb200_solve_entry(const sb200_matrix *m, const double *b, uint64_t blen,
     SB_TRY(copy_d2h(est, d_est.p, nqueries * 8, st));
     if (var) SB_TRY(copy_d2h(var, d_var.p, nqueries * 8, st));
     SB_CUDA(cudaStreamSynchronize(st));
-    return SB200_OK;
-}
-
-// computePageRank (ref src/core/solver.ts:664-722): outdeg[i] = sum_j adj[i][j] (:679-684); S = I, then
-// S[i][j] -= alpha * adj[j][i] / outdeg[j] where outdeg[j] > 0 (:689-698) — dangling rows contribute nothing;
-// rhs = (1 - alpha)/n (:708).  adj is dense in the reference (one number per pair), so repeated edges and a
-// self loop's contribution to the diagonal are merged by summation (SB200_DUP_SUM).
-int32_t sb200_pagerank_system(const uint64_t *src, const uint64_t *dst, const double *w, uint64_t nedges, uint64_t n,
-                              double alpha, sb200_matrix **S, double *rhs) {
-    clear_error();
-    if (!S) return fail(SB200_ERR_INVALID_INPUT, "S is null");
-    *S = nullptr;
-    if (!(alpha >= 0.0 && alpha <= 1.0)) return fail(SB200_ERR_INVALID_INPUT, "damping must be in [0, 1]");  // validateRange (:666)
-    if (nedges && (!src || !dst)) return fail(SB200_ERR_INVALID_INPUT, "null edge list");
-    std::vector<double> outdeg(n, 0.0);
-    for (uint64_t e = 0; e < nedges; e++) {
-        if (src[e] >= n || dst[e] >= n)
-            return fail(SB200_ERR_INDEX_OUT_OF_BOUNDS, "edge %llu (%llu -> %llu) out of bounds for %llu nodes",
-                        (unsigned long long)e, (unsigned long long)src[e], (unsigned long long)dst[e], (unsigned long long)n);
-        outdeg[src[e]] += w ? w[e] : 1.0;
-    }
-    std::vector<uint64_t> tr, tc;
-    std::vector<double> tv;
-    tr.reserve(n + nedges);
-    tc.reserve(n + nedges);
-    tv.reserve(n + nedges);
-    for (uint64_t i = 0; i < n; i++) {
-        tr.push_back(i);
-        tc.push_back(i);
-        tv.push_back(1.0);
-    }
-    for (uint64_t e = 0; e < nedges; e++) {
-        const uint64_t j = src[e], i = dst[e];
-        if (outdeg[j] > 0.0) {
-            tr.push_back(i);
-            tc.push_back(j);
-            tv.push_back(-(alpha * ((w ? w[e] : 1.0) / outdeg[j])));
-        }
-    }
-    std::vector<uint64_t> rp;
-    std::vector<uint32_t> ci;
-    std::vector<double> cv;
-    SB_TRY(triplets_to_csr(tr.data(), tc.data(), tv.data(), tv.size(), n, n, SB200_DUP_SUM, rp, ci, cv));
-    SB_TRY(matrix_from_host_csr(rp.data(), nullptr, ci.data(), cv.data(), n, n, rp[n], false, S));
-    if (rhs)
-        for (uint64_t i = 0; i < n; i++) rhs[i] = (1.0 - alpha) / (double)n;
     return SB200_OK;
 }
 

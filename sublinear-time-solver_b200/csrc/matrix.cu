@@ -320,28 +320,72 @@ int32_t matrix_from_host_csr(const uint64_t *row_ptr64, const uint32_t *row_ptr3
     }
 
     SB_TRY(require_device(m->device));  // after host-side validation: input errors do not need a GPU to be reported
-    m->tile_cfg = default_tile_cfg();
-    std::vector<TileDesc> tiles;
-    build_tiles(rp, nrows, kTileCfgs[m->tile_cfg < 0 ? 0 : m->tile_cfg], tiles);  // unused by the warp-stream kernel
-    m->ntiles = (uint32_t)(tiles.size() - 1);
-
     // device arrays are padded so that the 16-byte-granular bulk copies may over-read past nnz
     const size_t nnz_pad = ((nnz + 3) & ~(size_t)3) + 8;
     SB_TRY(m->d_vals.alloc(nnz_pad));
     SB_TRY(m->d_cols.alloc(nnz_pad));
     SB_TRY(m->d_row_ptr.alloc(nrows + 1));
-    SB_TRY(m->d_tiles.alloc(tiles.size()));
     SB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     SB_CUDA(cudaMemsetAsync(m->d_vals.p + nnz, 0, (nnz_pad - nnz) * sizeof(double), m->stream));
     SB_CUDA(cudaMemsetAsync(m->d_cols.p + nnz, 0, (nnz_pad - nnz) * sizeof(uint32_t), m->stream));
     SB_TRY(copy_h2d(m->d_vals.p, vals, nnz * sizeof(double), m->stream));
     SB_TRY(copy_h2d(m->d_cols.p, cols, nnz * sizeof(uint32_t), m->stream));
     SB_TRY(copy_h2d(m->d_row_ptr.p, rp, (nrows + 1) * sizeof(uint32_t), m->stream));
+    SB_TRY(matrix_finish(m.get(), allow_slabs));
+    *out = m.release();
+    return SB200_OK;
+}
+
+// derived layouts of a handle whose CSR slices are resident (d_vals / d_cols padded, d_row_ptr, h_row_ptr, stream set)
+int32_t matrix_finish(sb200_matrix *m, bool allow_slabs) {
+    const uint32_t *rp = m->h_row_ptr.data();
+    m->tile_cfg = default_tile_cfg();
+    std::vector<TileDesc> tiles;
+    build_tiles(rp, m->nrows, kTileCfgs[m->tile_cfg < 0 ? 0 : m->tile_cfg], tiles);  // unused by the warp-stream kernel
+    m->ntiles = (uint32_t)(tiles.size() - 1);
+    SB_TRY(m->d_tiles.alloc(tiles.size()));
     SB_TRY(copy_h2d(m->d_tiles.p, tiles.data(), tiles.size() * sizeof(TileDesc), m->stream));
-    if (allow_slabs) SB_TRY(build_slabs(m.get()));
-    SB_TRY(build_long_rows(m.get()));
-    if (m->nslabs == 0) SB_TRY(build_sell(m.get()));
+    if (allow_slabs) SB_TRY(build_slabs(m));
+    SB_TRY(build_long_rows(m));
+    if (m->nslabs == 0) SB_TRY(build_sell(m));
     SB_CUDA(cudaStreamSynchronize(m->stream));
+    return SB200_OK;
+}
+
+// a handle over CSR slices that already live on the device (csrc/ingest.cu): takes ownership of nothing, copies the
+// slices into padded arrays of its own
+int32_t matrix_from_device_csr(const uint32_t *d_row_ptr, const uint32_t *d_cols, const double *d_vals, uint64_t nrows,
+                               uint64_t ncols, uint64_t nnz, cudaStream_t src_stream, sb200_matrix **out) {
+    if (!out) return fail(SB200_ERR_INVALID_INPUT, "out is null");
+    *out = nullptr;
+    if (nrows >= 0xFFFFFFF0ull || ncols >= 0xFFFFFFF0ull)
+        return fail(SB200_ERR_INVALID_INPUT, "dimension exceeds the u32 IndexType of the reference (src/types.rs:22)");
+    if (nnz >= 0xFFFFFFF0ull)
+        return fail(SB200_ERR_MEMORY_ALLOCATION,
+                    "nnz %llu does not fit the u32 row_ptr of CSRStorage (src/matrix/sparse.rs:22); "
+                    "row-partition the system across GPUs",
+                    (unsigned long long)nnz);
+    std::unique_ptr<sb200_matrix> m(new sb200_matrix());
+    m->device = current_device();
+    m->nrows = nrows;
+    m->ncols = ncols;
+    m->nnz = nnz;
+    m->n_global = ncols;
+    m->h_row_ptr.resize(nrows + 1);
+    const size_t nnz_pad = ((nnz + 3) & ~(size_t)3) + 8;
+    SB_TRY(m->d_vals.alloc(nnz_pad));
+    SB_TRY(m->d_cols.alloc(nnz_pad));
+    SB_TRY(m->d_row_ptr.alloc(nrows + 1));
+    SB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    SB_CUDA(cudaStreamSynchronize(src_stream));  // the producer's work on the source slices
+    SB_CUDA(cudaMemsetAsync(m->d_vals.p + nnz, 0, (nnz_pad - nnz) * sizeof(double), m->stream));
+    SB_CUDA(cudaMemsetAsync(m->d_cols.p + nnz, 0, (nnz_pad - nnz) * sizeof(uint32_t), m->stream));
+    SB_CUDA(cudaMemcpyAsync(m->d_vals.p, d_vals, nnz * sizeof(double), cudaMemcpyDeviceToDevice, m->stream));
+    SB_CUDA(cudaMemcpyAsync(m->d_cols.p, d_cols, nnz * sizeof(uint32_t), cudaMemcpyDeviceToDevice, m->stream));
+    SB_CUDA(cudaMemcpyAsync(m->d_row_ptr.p, d_row_ptr, (nrows + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, m->stream));
+    SB_TRY(copy_d2h(m->h_row_ptr.data(), d_row_ptr, (nrows + 1) * sizeof(uint32_t), m->stream));
+    SB_CUDA(cudaStreamSynchronize(m->stream));
+    SB_TRY(matrix_finish(m.get(), true));
     *out = m.release();
     return SB200_OK;
 }
@@ -429,91 +473,6 @@ int32_t matrix_analyse(sb200_matrix *m, int mode, bool need_cols, const ColReduc
     return SB200_OK;
 }
 
-// SparseMatrix::from_triplets (src/matrix/mod.rs:160-199) -> COOStorage::from_triplets (sparse.rs:528-548)
-// -> CSRStorage::from_coo (sparse.rs:80-132), restated as: validate in order, drop exact zeros, counting
-// sort by row (stable), stable sort of each row by column. Duplicates stay separate entries (or are summed).
-int32_t triplets_to_csr(const uint64_t *rows, const uint64_t *cols, const double *vals, uint64_t nt,
-                               uint64_t nrows, uint64_t ncols, int dup_policy, std::vector<uint64_t> &row_ptr,
-                               std::vector<uint32_t> &ci, std::vector<double> &cv) {
-    if (nt && (!rows || !cols || !vals)) return fail(SB200_ERR_INVALID_INPUT, "null triplet slice");
-    for (uint64_t i = 0; i < nt; i++) {
-        if (rows[i] >= nrows)
-            return fail(SB200_ERR_INDEX_OUT_OF_BOUNDS, "row index %llu out of bounds (max %llu) in triplet %llu",
-                        (unsigned long long)rows[i], (unsigned long long)(nrows ? nrows - 1 : 0), (unsigned long long)i);
-        if (cols[i] >= ncols)
-            return fail(SB200_ERR_INDEX_OUT_OF_BOUNDS, "column index %llu out of bounds (max %llu) in triplet %llu",
-                        (unsigned long long)cols[i], (unsigned long long)(ncols ? ncols - 1 : 0), (unsigned long long)i);
-        if (!std::isfinite(vals[i]))
-            return fail(SB200_ERR_INVALID_INPUT, "Non-finite value %g at (%llu, %llu)", vals[i],
-                        (unsigned long long)rows[i], (unsigned long long)cols[i]);
-    }
-    row_ptr.assign(nrows + 1, 0);
-    for (uint64_t i = 0; i < nt; i++)
-        if (vals[i] != 0.0) row_ptr[rows[i] + 1]++;
-    for (uint64_t r = 0; r < nrows; r++) row_ptr[r + 1] += row_ptr[r];
-    const uint64_t nnz = row_ptr[nrows];
-    ci.resize(nnz);
-    cv.resize(nnz);
-    {
-        std::vector<uint64_t> cur(row_ptr.begin(), row_ptr.end() - 1);
-        for (uint64_t i = 0; i < nt; i++)
-            if (vals[i] != 0.0) {
-                const uint64_t p = cur[rows[i]]++;
-                ci[p] = (uint32_t)cols[i];
-                cv[p] = vals[i];
-            }
-    }
-#pragma omp parallel
-    {
-        std::vector<std::pair<uint32_t, double>> tmp;
-#pragma omp for schedule(dynamic, 1024)
-        for (long long r = 0; r < (long long)nrows; r++) {
-            const uint64_t s = row_ptr[r], e = row_ptr[r + 1];
-            bool sorted = true;
-            for (uint64_t k = s + 1; k < e; k++)
-                if (ci[k - 1] > ci[k]) { sorted = false; break; }
-            if (sorted) continue;
-            if (e - s <= 32) {  // stable insertion sort
-                for (uint64_t a = s + 1; a < e; a++) {
-                    const uint32_t cc = ci[a];
-                    const double vv = cv[a];
-                    uint64_t p = a;
-                    while (p > s && ci[p - 1] > cc) { ci[p] = ci[p - 1]; cv[p] = cv[p - 1]; p--; }
-                    ci[p] = cc;
-                    cv[p] = vv;
-                }
-            } else {
-                tmp.resize(e - s);
-                for (uint64_t k = s; k < e; k++) tmp[k - s] = {ci[k], cv[k]};
-                std::stable_sort(tmp.begin(), tmp.end(),
-                                 [](const std::pair<uint32_t, double> &a, const std::pair<uint32_t, double> &b) {
-                                     return a.first < b.first;
-                                 });
-                for (uint64_t k = s; k < e; k++) { ci[k] = tmp[k - s].first; cv[k] = tmp[k - s].second; }
-            }
-        }
-    }
-    if (dup_policy == SB200_DUP_SUM) {
-        uint64_t w = 0;
-        std::vector<uint64_t> nrp(nrows + 1, 0);
-        for (uint64_t r = 0; r < nrows; r++) {
-            uint64_t k = row_ptr[r];
-            const uint64_t e = row_ptr[r + 1];
-            while (k < e) {
-                const uint32_t c = ci[k];
-                double acc = cv[k++];
-                while (k < e && ci[k] == c) acc += cv[k++];
-                if (acc != 0.0) { ci[w] = c; cv[w] = acc; w++; }
-            }
-            nrp[r + 1] = w;
-        }
-        row_ptr.swap(nrp);
-        ci.resize(w);
-        cv.resize(w);
-    }
-    return SB200_OK;
-}
-
 }  // namespace sb200
 
 // -------------------------------------------------------------------------------------------------------------
@@ -527,11 +486,10 @@ int32_t sb200_matrix_from_triplets_ex(const uint64_t *rows, const uint64_t *cols
     clear_error();
     if (!out) return fail(SB200_ERR_INVALID_INPUT, "out is null");
     *out = nullptr;
-    std::vector<uint64_t> rp;
-    std::vector<uint32_t> ci;
-    std::vector<double> cv;
-    SB_TRY(triplets_to_csr(rows, cols, vals, ntriplets, nrows, ncols, dup_policy, rp, ci, cv));
-    return matrix_from_host_csr(rp.data(), nullptr, ci.data(), cv.data(), nrows, ncols, rp[nrows], false, out);
+    // SparseMatrix::from_triplets (src/matrix/mod.rs:160-199): validated on the host in triplet order, converted on the
+    // device (csrc/ingest.cu)
+    SB_TRY(validate_triplets(rows, cols, vals, ntriplets, nrows, ncols));
+    return matrix_from_triplets_device(rows, cols, vals, ntriplets, nrows, ncols, dup_policy, out);
 }
 
 int32_t sb200_matrix_from_triplets(const uint64_t *rows, const uint64_t *cols, const double *vals,

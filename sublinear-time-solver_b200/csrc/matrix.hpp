@@ -101,6 +101,15 @@ int32_t matrix_from_host_csr(const uint64_t *row_ptr64, const uint32_t *row_ptr3
 // reduce_cols (row-partitioned handles): sums the per-column |diagonal| and off-diagonal accumulators over all ranks
 // before the column-dominance test, so that every rank sees whole columns
 using ColReduce = std::function<int32_t(double *col_diag, double *col_off, uint64_t ncols, cudaStream_t st)>;
+int32_t matrix_finish(sb200_matrix *m, bool allow_slabs);
+int32_t matrix_from_device_csr(const uint32_t *d_row_ptr, const uint32_t *d_cols, const double *d_vals, uint64_t nrows,
+                               uint64_t ncols, uint64_t nnz, cudaStream_t src_stream, sb200_matrix **out);
+// COO -> CSR on the device (csrc/ingest.cu): SparseMatrix::from_triplets semantics (zeros dropped, stable (row, col) order,
+// duplicates kept or summed in triplet order). Host slices, already validated.
+int32_t matrix_from_triplets_device(const uint64_t *rows, const uint64_t *cols, const double *vals, uint64_t nt,
+                                    uint64_t nrows, uint64_t ncols, int dup_policy, sb200_matrix **out);
+int32_t validate_triplets(const uint64_t *rows, const uint64_t *cols, const double *vals, uint64_t nt, uint64_t nrows,
+                          uint64_t ncols);
 int32_t matrix_analyse(sb200_matrix *m, int mode, bool need_cols, const ColReduce &reduce_cols = ColReduce());
 int32_t matrix_spmv_dev(const sb200_matrix *m, const double *x_dev, double *y_dev, int accumulate, cudaStream_t st);
 void matrix_retain(sb200_matrix *m);

@@ -167,8 +167,12 @@ def test_hub_rows_in_every_layout(oracle, monkeypatch, layout):
     lens = np.diff(A.row_ptr.astype(np.int64))
     short = lens <= 1024
     assert (~short).sum() == len(hubs)
-    assert np.array_equal(y[short], ref[short])
-    np.testing.assert_allclose(y[~short], ref[~short], rtol=1e-11, atol=1e-11)
+    exact = short.copy()
+    if layout == "csr":       # the warp-stream kernel sums every row of a hub's 32-row block lane-strided
+        for h in np.nonzero(~short)[0]:
+            exact[(h // 32) * 32:(h // 32) * 32 + 32] = False
+    assert np.array_equal(y[exact], ref[exact])
+    np.testing.assert_allclose(y[~exact], ref[~exact], rtol=1e-11, atol=1e-11)
     y0 = rng.standard_normal(n)
     ya = m.multiply_vector_add(x, y0)
     np.testing.assert_allclose(ya, y0 + ref, rtol=1e-11, atol=1e-10)
