@@ -429,6 +429,24 @@ int32_t sb200_forward_push_solve(const sb200_matrix *m, const double *b, uint64_
                                  uint64_t max_iterations, double *x_out, sb200_axb_push_stats *stats);
 
 /* ---------------------------------------------------------------------------------------------- */
+/* StreamingMatrix (src/matrix/optimized.rs:451-561)                             */
+/* ---------------------------------------------------------------------------------------------- */
+/* Row chunks sized from a memory limit (chunk_size = min(rows, max(1, limit / (2 (12 nt / rows + 4))))), kept in pinned
+ * host memory; multiply_vector_streaming uploads chunk k + 1 while chunk k is multiplied on the GPU and hands every
+ * chunk's slice of y to the callback in row order. Triplet semantics as SparseMatrix::from_triplets. */
+typedef struct sb200_streaming_matrix sb200_streaming_matrix;
+/* start_row, the chunk's slice of A x, its length; a non-zero return stops the walk (extension). */
+typedef int32_t (*sb200_chunk_callback)(uint64_t start_row, const double *result, uint64_t len, void *user);
+int32_t sb200_streaming_matrix_from_triplets(const uint64_t *rows, const uint64_t *cols, const double *vals, uint64_t ntriplets,
+                                             uint64_t nrows, uint64_t ncols, uint64_t memory_limit_mb,
+                                             sb200_streaming_matrix **out);
+int32_t sb200_streaming_matrix_info(const sb200_streaming_matrix *sm, uint64_t *total_rows, uint64_t *total_cols,
+                                    uint64_t *chunk_size, uint64_t *num_chunks, uint64_t *memory_usage);
+int32_t sb200_streaming_matrix_multiply_vector(const sb200_streaming_matrix *sm, const double *x, uint64_t xlen,
+                                               sb200_chunk_callback callback, void *user);
+void sb200_streaming_matrix_free(sb200_streaming_matrix *sm);
+
+/* ---------------------------------------------------------------------------------------------- */
 /* single-entry estimation and PageRank (TS-only front doors)               */
 /* ---------------------------------------------------------------------------------------------- */
 /* Batched estimate of x[rows[q]] for A x = b by absorbing random walks (Ulam-von Neumann estimator,

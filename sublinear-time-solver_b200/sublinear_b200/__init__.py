@@ -66,6 +66,7 @@ class _Partial(C.Structure):
 
 
 _STREAM_CB = C.CFUNCTYPE(C.c_int32, C.POINTER(_Partial), C.c_void_p)
+_CHUNK_CB = C.CFUNCTYPE(C.c_int32, C.c_uint64, C.POINTER(C.c_double), C.c_uint64, C.c_void_p)
 
 
 class _PushConfig(C.Structure):
@@ -202,6 +203,10 @@ def lib():
         "sb200_bidirectional_push": ([vp, P(_PushConfig), P(_PushConfig), u64, u64, P(f64)], i32),
         "sb200_bidirectional_adaptive_push": ([vp, P(_PushConfig), P(_PushConfig), u64, u64, P(f64)], i32),
         "sb200_forward_push_solve": ([vp, vp, u64, f64, u64, vp, P(_AxbPushStats)], i32),
+        "sb200_streaming_matrix_from_triplets": ([vp, vp, vp, u64, u64, u64, u64, P(vp)], i32),
+        "sb200_streaming_matrix_info": ([vp, P(u64), P(u64), P(u64), P(u64), P(u64)], i32),
+        "sb200_streaming_matrix_multiply_vector": ([vp, vp, u64, _CHUNK_CB, vp], i32),
+        "sb200_streaming_matrix_free": ([vp], None),
         "sb200_cg_config_default": ([P(_CgConfig)], None),
         "sb200_cg_solve": ([vp, vp, u64, P(_CgConfig), P(_CgResult)], i32),
         "sb200_cg_solve_into": ([vp, vp, u64, P(_CgConfig), vp, P(_CgResult)], i32),
@@ -972,6 +977,55 @@ def forward_push_solve(matrix: "SparseMatrix", b, epsilon=1e-6, max_iterations=1
     res = ForwardPushSolveResult(x, int(st.iterations), st.residual_norm, bool(st.converged), int(st.rounds), st.max_residual)
     _check(rc, res)
     return res
+
+
+class StreamingMatrix:
+    """`StreamingMatrix` (src/matrix/optimized.rs:451-561): row chunks sized from a memory limit, held in pinned host
+    memory and streamed through the GPU."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.sb200_streaming_matrix_free(self._h)
+            self._h = None
+
+    @staticmethod
+    def from_triplets(rows, cols, vals, nrows, ncols, memory_limit_mb) -> "StreamingMatrix":
+        r, c, v = _u64(rows), _u64(cols), _f64(vals)
+        h = C.c_void_p()
+        _check(lib().sb200_streaming_matrix_from_triplets(_ptr(r), _ptr(c), _ptr(v), len(v), nrows, ncols, memory_limit_mb,
+                                                          C.byref(h)))
+        return StreamingMatrix(h)
+
+    def info(self) -> dict:
+        v = [C.c_uint64() for _ in range(5)]
+        _check(lib().sb200_streaming_matrix_info(self._h, *[C.byref(t) for t in v]))
+        return dict(zip(("total_rows", "total_cols", "chunk_size", "num_chunks", "memory_usage"), (t.value for t in v)))
+
+    def memory_usage(self) -> int:
+        return self.info()["memory_usage"]
+
+    def multiply_vector_streaming(self, x, callback) -> None:
+        """`multiply_vector_streaming(x, |start_row, result| ..)`; callback(start_row, result) may return True to stop"""
+        x = _f64(x)
+
+        def _cb(start, ptr, n, _user):
+            stop = callback(int(start), np.ctypeslib.as_array(ptr, shape=(max(int(n), 1),))[:int(n)].copy())
+            return 1 if stop else 0
+
+        cb = _CHUNK_CB(_cb)
+        _check(lib().sb200_streaming_matrix_multiply_vector(self._h, _ptr(x), len(x), cb, None))
+
+    def multiply_vector(self, x) -> np.ndarray:
+        y = np.zeros(self.info()["total_rows"])
+
+        def put(start, part):
+            y[start:start + len(part)] = part
+
+        self.multiply_vector_streaming(x, put)
+        return y
 
 
 def push_iterations_dev(matrix: SparseMatrix, b_ptr: int, n: int, nterms: int, x_ptr: int = 0, t_ptr: int = 0,

@@ -236,3 +236,46 @@ def test_gpu_state_outlives_matrix_handle(oracle):
         assert st.step() == ost.step()
     assert np.array_equal(st.extract_solution(), ost.extract_solution())
     del st                                               # the last owner frees the matrix
+
+
+@pytest.mark.gpu
+def test_streaming_matrix_row_chunks(oracle):
+    """StreamingMatrix (src/matrix/optimized.rs:451-561): chunk size from the memory limit, chunks visited in row order,
+    every slice bit-identical to the oracle's SpMV over the whole matrix; memory_usage = sum(nnz * 12 + rows * 4)"""
+    O = oracle
+    rng = np.random.default_rng(21)
+    nr, nc, nt = 50_000, 40_000, 600_000
+    rows, cols = rng.integers(0, nr, nt), rng.integers(0, nc, nt)
+    vals = rng.standard_normal(nt)
+    vals[::97] = 0.0                                                     # exact zeros are dropped
+    A = O.Csr.from_triplets(rows, cols, vals, nr, nc)
+    sm = sb.StreamingMatrix.from_triplets(rows, cols, vals, nr, nc, memory_limit_mb=1)
+    info = sm.info()
+    avg = nt // nr
+    want_chunk = min(nr, max(1, (1 << 20) // ((avg * 12 + 4) * 2)))      # optimized.rs:470-482
+    assert info["chunk_size"] == want_chunk and info["num_chunks"] == -(-nr // want_chunk) and info["num_chunks"] > 5
+    assert info["memory_usage"] == A.nnz * 12 + nr * 4
+    x = rng.standard_normal(nc)
+    seen = []
+    y = np.full(nr, np.nan)
+
+    def cb(start, part):
+        seen.append((start, len(part)))
+        y[start:start + len(part)] = part
+
+    sm.multiply_vector_streaming(x, cb)
+    assert [s for s, _ in seen] == [k * want_chunk for k in range(info["num_chunks"])]
+    assert sum(n for _, n in seen) == nr
+    assert np.array_equal(y, A.multiply_vector(x))
+    assert np.array_equal(sm.multiply_vector(x), y)
+    stops = []
+    sm.multiply_vector_streaming(x, lambda s, p: stops.append(s) or len(stops) == 3)      # the callback may stop the walk
+    assert len(stops) == 3
+    one = sb.StreamingMatrix.from_triplets(rows, cols, vals, nr, nc, memory_limit_mb=4096)  # everything fits: one chunk
+    assert one.info()["num_chunks"] == 1 and np.array_equal(one.multiply_vector(x), y)
+    with pytest.raises(sb.SolverError) as ei:
+        sm.multiply_vector(np.ones(nc + 1))
+    assert ei.value.variant == "DimensionMismatch"
+    with pytest.raises(sb.SolverError) as ei:
+        sb.StreamingMatrix.from_triplets([nr], [0], [1.0], nr, nc, 1)
+    assert ei.value.variant == "IndexOutOfBounds"
