@@ -443,6 +443,18 @@ inline PushResult run_push(Fn fn, const PushGraph &g, const PushConfig &cfg, con
     r.push_count = st.push_count; r.nodes_visited = st.nodes_visited; r.residual_norm = st.residual_norm;
     return r;
 }
+template <typename Fn>
+inline PushResult run_push_watch(Fn fn, const PushGraph &g, const PushConfig &cfg, size_t source, size_t target,
+                                 Precision precision) {
+    const sb200_push_config c = cfg.to_c();
+    PushResult r;
+    r.estimate.assign(g.num_nodes(), 0.0);
+    r.residual.assign(g.num_nodes(), 0.0);
+    sb200_push_stats st;
+    check(fn(g.handle(), &c, source, target, precision, r.estimate.data(), r.residual.data(), &st));
+    r.push_count = st.push_count; r.nodes_visited = st.nodes_visited; r.residual_norm = st.residual_norm;
+    return r;
+}
 }  // namespace detail
 
 class ForwardPushSolver {  // forward_push.rs:52-328
@@ -459,6 +471,11 @@ public:
         for (size_t i = 0; i < x.size(); i++) x[i] += config_.alpha * result.residual[i];
         return x;
     }
+    PushResult solve_with_target(size_t source, size_t target, Precision target_precision) const {  // :234-290
+        return detail::run_push_watch(sb200_forward_push_with_target, graph_, config_, source, target, target_precision);
+    }
+    const PushGraph &graph() const { return graph_; }
+    const PushConfig &config() const { return config_; }
 
 private:
     PushGraph graph_;
@@ -474,10 +491,113 @@ public:
         const PushResult r = solve_single_target(target);
         return source < r.estimate.size() ? r.estimate[source] : 0.0;
     }
+    PushResult solve_with_source(size_t source, size_t target, Precision source_precision) const {  // :238-290
+        return detail::run_push_watch(sb200_backward_push_with_source, graph_, config_, source, target, source_precision);
+    }
+    std::vector<Precision> extrapolated_solution(const PushResult &result) const {  // :300-309
+        std::vector<Precision> x = result.estimate;
+        for (size_t i = 0; i < x.size(); i++) x[i] += config_.alpha * result.residual[i];
+        return x;
+    }
+    std::vector<Precision> reachability_probabilities(size_t target) const {  // :294-297
+        return extrapolated_solution(solve_single_target(target));
+    }
+    Precision combine_with_forward(const PushResult &backward_result, const std::vector<Precision> &forward_estimate,
+                                   const std::vector<Precision> &forward_residual) const {  // :312-330
+        double out = 0.0;
+        detail::check(sb200_push_combine_with_forward(config_.alpha, backward_result.estimate.data(), backward_result.residual.data(),
+                                                      backward_result.estimate.size(), forward_estimate.data(),
+                                                      forward_residual.data(), forward_estimate.size(), &out));
+        return out;
+    }
+    const PushGraph &graph() const { return graph_; }
 
 private:
     PushGraph graph_;
     PushConfig config_;
+};
+
+// BidirectionalPushSolver (backward_push.rs:338-420). The reference clones the graph into two solvers; here both
+// directions run on the one device-resident PushGraph.
+class BidirectionalPushSolver {
+public:
+    BidirectionalPushSolver(PushGraph graph, PushConfig forward_config = {}, PushConfig backward_config = {})
+        : graph_(std::move(graph)), forward_(forward_config), backward_(backward_config) {}
+    Precision solve_bidirectional(size_t source, size_t target) const {
+        const sb200_push_config f = forward_.to_c(), b = backward_.to_c();
+        double out = 0.0;
+        detail::check(sb200_bidirectional_push(graph_.handle(), &f, &b, source, target, &out));
+        return out;
+    }
+    Precision adaptive_solve(size_t source, size_t target) const {
+        const sb200_push_config f = forward_.to_c(), b = backward_.to_c();
+        double out = 0.0;
+        detail::check(sb200_bidirectional_adaptive_push(graph_.handle(), &f, &b, source, target, &out));
+        return out;
+    }
+
+private:
+    PushGraph graph_;
+    PushConfig forward_, backward_;
+};
+
+// SublinearSolver.solveForwardPush of the TS package (src/core/solver.ts:437-522): A x = b by residual pushes
+struct ForwardPushSolveResult {
+    std::vector<Precision> solution;
+    size_t iterations = 0;
+    Precision residual = 0.0;
+    bool converged = false;
+};
+inline ForwardPushSolveResult forward_push_solve(const SparseMatrix &matrix, const std::vector<Precision> &b,
+                                                 Precision epsilon = 1e-6, size_t max_iterations = 1000) {
+    ForwardPushSolveResult r;
+    r.solution.assign(b.size(), 0.0);
+    sb200_axb_push_stats st;
+    detail::check(sb200_forward_push_solve(matrix.handle(), b.data(), b.size(), epsilon, max_iterations, r.solution.data(), &st));
+    r.iterations = st.iterations;
+    r.residual = st.residual_norm;
+    r.converged = st.converged != 0;
+    return r;
+}
+
+// StreamingMatrix (src/matrix/optimized.rs:451-561): row chunks in pinned host memory, streamed through the GPU
+class StreamingMatrix {
+public:
+    static StreamingMatrix from_triplets(const std::vector<std::tuple<size_t, size_t, Precision>> &triplets, size_t rows,
+                                         size_t cols, size_t memory_limit_mb) {
+        std::vector<uint64_t> r(triplets.size()), c(triplets.size());
+        std::vector<double> v(triplets.size());
+        for (size_t i = 0; i < triplets.size(); i++) { r[i] = std::get<0>(triplets[i]); c[i] = std::get<1>(triplets[i]); v[i] = std::get<2>(triplets[i]); }
+        sb200_streaming_matrix *h = nullptr;
+        detail::check(sb200_streaming_matrix_from_triplets(r.data(), c.data(), v.data(), v.size(), rows, cols, memory_limit_mb, &h));
+        return StreamingMatrix(h);
+    }
+    StreamingMatrix(StreamingMatrix &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    StreamingMatrix(const StreamingMatrix &) = delete;
+    ~StreamingMatrix() { sb200_streaming_matrix_free(h_); }
+    // multiply_vector_streaming(x, |start_row, result| ..)
+    template <typename F>
+    void multiply_vector_streaming(const std::vector<Precision> &x, F callback) const {
+        auto tramp = [](uint64_t start, const double *res, uint64_t len, void *user) -> int32_t {
+            (*static_cast<F *>(user))(static_cast<size_t>(start), res, static_cast<size_t>(len));
+            return 0;
+        };
+        detail::check(sb200_streaming_matrix_multiply_vector(h_, x.data(), x.size(), tramp, &callback));
+    }
+    size_t memory_usage() const {
+        uint64_t b = 0;
+        detail::check(sb200_streaming_matrix_info(h_, nullptr, nullptr, nullptr, nullptr, &b));
+        return b;
+    }
+    size_t num_chunks() const {
+        uint64_t k = 0;
+        detail::check(sb200_streaming_matrix_info(h_, nullptr, nullptr, nullptr, &k, nullptr));
+        return k;
+    }
+
+private:
+    explicit StreamingMatrix(sb200_streaming_matrix *h) : h_(h) {}
+    sb200_streaming_matrix *h_ = nullptr;
 };
 
 }  // namespace sublinear

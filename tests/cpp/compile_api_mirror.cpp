@@ -21,7 +21,19 @@ int use_everything(bool run) {
     auto fr = f.solve_single_source(0);
     (void)f.solve_multi_source({0, 1}); (void)f.query_single_entry(0, 1); (void)f.extrapolated_solution(fr);
     BackwardPushSolver b(std::move(g));
-    (void)b.solve_single_target(0); (void)b.solve_multi_target({0, 1}); (void)b.query_transition_probability(0, 1);
+    auto br = b.solve_single_target(0);
+    (void)b.solve_multi_target({0, 1}); (void)b.query_transition_probability(0, 1);
+    (void)f.solve_with_target(0, 1, 1e-3); (void)b.solve_with_source(0, 1, 1e-3);
+    (void)b.extrapolated_solution(br); (void)b.reachability_probabilities(1);
+    (void)b.combine_with_forward(br, fr.estimate, fr.residual);
+    BidirectionalPushSolver bi(PushGraph::from_edges(2, {{0, 1, 1.0}}));
+    (void)bi.solve_bidirectional(0, 1); (void)bi.adaptive_solve(0, 1);
+    auto fp = forward_push_solve(m, {5.0, 4.0}, 1e-8, 1000);
+    (void)fp.converged;
+    auto sm = StreamingMatrix::from_triplets({{0, 0, 4.0}, {1, 1, 3.0}}, 2, 2, 1);
+    size_t seen = 0;
+    sm.multiply_vector_streaming({1.0, 1.0}, [&](size_t, const double *, size_t len) { seen += len; });
+    (void)sm.memory_usage(); (void)sm.num_chunks();
     auto om = OptimizedSparseMatrix::from_triplets({{0, 0, 4.0}}, 1, 1);
     OptimizedConjugateGradientSolver cg;
     (void)cg.solve(om, {1.0});
