@@ -238,10 +238,12 @@ __global__ void __launch_bounds__(NT) warp_kernel(const TileKernelArgs a) {
 
 template <int EPI, int NT, int EPL>
 static int32_t launch_warp_one(const TileKernelArgs &a, cudaStream_t stream, int *max_grid_out) {
-    static int max_grid[16] = {0};
+    static int max_grid[64] = {0};
+    static std::mutex mu;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 16) return fail(SB200_ERR_ALGORITHM, "device index %d out of range", dev);
+    if (dev < 0 || dev >= 64) return fail(SB200_ERR_ALGORITHM, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(mu);  // the occupancy cache is filled once per device
     if (max_grid[dev] == 0) {
         int per_sm = 0, sms = 0;
         SB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, warp_kernel<EPI, NT, EPL>, NT, 0));
@@ -434,10 +436,12 @@ constexpr int kSellThreads = 256;
 
 template <int EPI, int U>
 static int32_t launch_sell_one(const TileKernelArgs &a, cudaStream_t stream, int *max_grid_out) {
-    static int max_grid[16] = {0};
+    static int max_grid[64] = {0};
+    static std::mutex mu;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 16) return fail(SB200_ERR_ALGORITHM, "device index %d out of range", dev);
+    if (dev < 0 || dev >= 64) return fail(SB200_ERR_ALGORITHM, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lk(mu);  // the occupancy cache is filled once per device
     if (max_grid[dev] == 0) {
         // no shared memory: ask for the smallest carve-out so the whole 256 KB array serves as L1
         SB_CUDA(cudaFuncSetAttribute(sell_kernel<EPI, kSellThreads, U>, cudaFuncAttributePreferredSharedMemoryCarveout,

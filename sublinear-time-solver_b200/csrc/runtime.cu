@@ -74,20 +74,47 @@ static bool is_pinned_or_device(const void *p) {
 }
 
 namespace {
+// Pageable host memory is staged through two pinned buffers per DEVICE (events belong to the device they were created
+// on; one process may drive several GPUs), each ring with its own lock so that solves on different GPUs do not serialise.
 struct StagingRing {
-    static constexpr size_t kChunk = 8u << 20;
+    static constexpr size_t kChunk = 16u << 20;
     void *buf[2] = {nullptr, nullptr};
     cudaEvent_t ev[2] = {nullptr, nullptr};
     std::mutex mu;
     int32_t ensure() {
         for (int i = 0; i < 2; i++) {
-            if (!buf[i]) SB_CUDA(cudaHostAlloc(&buf[i], kChunk, cudaHostAllocDefault));
+            if (!buf[i]) SB_CUDA(cudaHostAlloc(&buf[i], kChunk, cudaHostAllocPortable));
             if (!ev[i]) SB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
         }
         return SB200_OK;
     }
 };
-StagingRing g_ring;
+constexpr int kMaxDevices = 64;
+StagingRing g_rings[kMaxDevices];
+
+StagingRing *ring_of_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return &g_rings[dev];
+}
+
+// host-side copy into / out of the pinned slot on a few threads (one thread moves ~10 GB/s, PCIe Gen5 takes ~50)
+void par_memcpy(void *dst, const void *src, size_t n) {
+    constexpr size_t kPiece = 1u << 20;
+    const long long pieces = (long long)((n + kPiece - 1) / kPiece);
+    if (pieces <= 2) {
+        memcpy(dst, src, n);
+        return;
+    }
+#pragma omp parallel for schedule(static) num_threads(4)
+    for (long long p = 0; p < pieces; p++) {
+        const size_t off = (size_t)p * kPiece;
+        memcpy((char *)dst + off, (const char *)src + off, n - off < kPiece ? n - off : kPiece);
+    }
+}
 }  // namespace
 
 int32_t copy_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t stream) {
@@ -96,19 +123,21 @@ int32_t copy_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t
         SB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyDefault, stream));
         return SB200_OK;
     }
-    std::lock_guard<std::mutex> lk(g_ring.mu);
-    SB_TRY(g_ring.ensure());
+    StagingRing *ring = ring_of_current_device();
+    if (!ring) return fail(SB200_ERR_ALGORITHM, "no current CUDA device for a staged copy");
+    std::lock_guard<std::mutex> lk(ring->mu);
+    SB_TRY(ring->ensure());
     size_t off = 0;
     for (int i = 0; off < bytes; i ^= 1) {
         size_t n = bytes - off < StagingRing::kChunk ? bytes - off : StagingRing::kChunk;
-        SB_CUDA(cudaEventSynchronize(g_ring.ev[i]));  // previous DMA out of this slot finished
-        memcpy(g_ring.buf[i], (const char *)src_host + off, n);
-        SB_CUDA(cudaMemcpyAsync((char *)dst_dev + off, g_ring.buf[i], n, cudaMemcpyHostToDevice, stream));
-        SB_CUDA(cudaEventRecord(g_ring.ev[i], stream));
+        SB_CUDA(cudaEventSynchronize(ring->ev[i]));  // previous DMA out of this slot finished
+        par_memcpy(ring->buf[i], (const char *)src_host + off, n);
+        SB_CUDA(cudaMemcpyAsync((char *)dst_dev + off, ring->buf[i], n, cudaMemcpyHostToDevice, stream));
+        SB_CUDA(cudaEventRecord(ring->ev[i], stream));
         off += n;
     }
-    SB_CUDA(cudaEventSynchronize(g_ring.ev[0]));
-    SB_CUDA(cudaEventSynchronize(g_ring.ev[1]));
+    SB_CUDA(cudaEventSynchronize(ring->ev[0]));
+    SB_CUDA(cudaEventSynchronize(ring->ev[1]));
     return SB200_OK;
 }
 
@@ -119,17 +148,19 @@ int32_t copy_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t
         SB_CUDA(cudaStreamSynchronize(stream));
         return SB200_OK;
     }
-    std::lock_guard<std::mutex> lk(g_ring.mu);
-    SB_TRY(g_ring.ensure());
+    StagingRing *ring = ring_of_current_device();
+    if (!ring) return fail(SB200_ERR_ALGORITHM, "no current CUDA device for a staged copy");
+    std::lock_guard<std::mutex> lk(ring->mu);
+    SB_TRY(ring->ensure());
     size_t off = 0, prev_off = 0, prev_n = 0;
     int prev = -1;
     for (int i = 0; off < bytes; i ^= 1) {
         size_t n = bytes - off < StagingRing::kChunk ? bytes - off : StagingRing::kChunk;
-        SB_CUDA(cudaMemcpyAsync(g_ring.buf[i], (const char *)src_dev + off, n, cudaMemcpyDeviceToHost, stream));
-        SB_CUDA(cudaEventRecord(g_ring.ev[i], stream));
+        SB_CUDA(cudaMemcpyAsync(ring->buf[i], (const char *)src_dev + off, n, cudaMemcpyDeviceToHost, stream));
+        SB_CUDA(cudaEventRecord(ring->ev[i], stream));
         if (prev >= 0) {
-            SB_CUDA(cudaEventSynchronize(g_ring.ev[prev]));
-            memcpy((char *)dst_host + prev_off, g_ring.buf[prev], prev_n);
+            SB_CUDA(cudaEventSynchronize(ring->ev[prev]));
+            par_memcpy((char *)dst_host + prev_off, ring->buf[prev], prev_n);
         }
         prev = i;
         prev_off = off;
@@ -137,8 +168,8 @@ int32_t copy_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t
         off += n;
     }
     if (prev >= 0) {
-        SB_CUDA(cudaEventSynchronize(g_ring.ev[prev]));
-        memcpy((char *)dst_host + prev_off, g_ring.buf[prev], prev_n);
+        SB_CUDA(cudaEventSynchronize(ring->ev[prev]));
+        par_memcpy((char *)dst_host + prev_off, ring->buf[prev], prev_n);
     }
     return SB200_OK;
 }
