@@ -23,8 +23,15 @@ pub struct sb200_push_config {
 #[repr(C)]
 pub struct sb200_push_stats {
     pub push_count: u64, pub nodes_visited: u64, pub residual_norm: f64, pub rounds: u64, pub kernel_launches: u64,
-    pub device_time_ms: f64,
+    pub device_time_ms: f64, pub dense_rounds: u64, pub edges_touched: u64,
 }
+
+#[repr(C)]
+pub struct sb200_axb_push_stats {
+    pub iterations: u64, pub rounds: u64, pub residual_norm: f64, pub max_residual: f64, pub converged: i32, pub reserved: i32,
+}
+
+#[repr(C)] pub struct sb200_streaming_matrix { _private: [u8; 0] }
 
 #[repr(C)]
 pub struct sb200_state_info_t {
@@ -94,6 +101,33 @@ extern "C" {
                           estimate: *mut f64, residual: *mut f64, stats: *mut sb200_push_stats) -> i32;
     fn sb200_backward_push(g: *const sb200_push_graph, cfg: *const sb200_push_config, targets: *const u64, ntargets: u64,
                            estimate: *mut f64, residual: *mut f64, stats: *mut sb200_push_stats) -> i32;
+    // solve_with_target / solve_with_source / combine_with_forward / BidirectionalPushSolver
+    // (src/solver/forward_push.rs:234-290, backward_push.rs:238-420)
+    fn sb200_forward_push_with_target(g: *const sb200_push_graph, cfg: *const sb200_push_config, source: u64, target: u64,
+                                      target_precision: f64, estimate: *mut f64, residual: *mut f64,
+                                      stats: *mut sb200_push_stats) -> i32;
+    fn sb200_backward_push_with_source(g: *const sb200_push_graph, cfg: *const sb200_push_config, source: u64, target: u64,
+                                       source_precision: f64, estimate: *mut f64, residual: *mut f64,
+                                       stats: *mut sb200_push_stats) -> i32;
+    fn sb200_push_combine_with_forward(alpha: f64, backward_estimate: *const f64, backward_residual: *const f64, nbackward: u64,
+                                       forward_estimate: *const f64, forward_residual: *const f64, nforward: u64,
+                                       out: *mut f64) -> i32;
+    fn sb200_bidirectional_push(g: *const sb200_push_graph, forward_cfg: *const sb200_push_config,
+                                backward_cfg: *const sb200_push_config, source: u64, target: u64, out: *mut f64) -> i32;
+    fn sb200_bidirectional_adaptive_push(g: *const sb200_push_graph, forward_cfg: *const sb200_push_config,
+                                         backward_cfg: *const sb200_push_config, source: u64, target: u64, out: *mut f64) -> i32;
+    // SublinearSolver.solveForwardPush of the TS package (src/core/solver.ts:437-522)
+    fn sb200_forward_push_solve(m: *const sb200_matrix, b: *const f64, blen: u64, epsilon: f64, max_iterations: u64,
+                                x_out: *mut f64, stats: *mut sb200_axb_push_stats) -> i32;
+    // StreamingMatrix (src/matrix/optimized.rs:451-561)
+    fn sb200_streaming_matrix_from_triplets(rows: *const u64, cols: *const u64, vals: *const f64, ntriplets: u64, nrows: u64,
+                                            ncols: u64, memory_limit_mb: u64, out: *mut *mut sb200_streaming_matrix) -> i32;
+    fn sb200_streaming_matrix_info(sm: *const sb200_streaming_matrix, total_rows: *mut u64, total_cols: *mut u64,
+                                   chunk_size: *mut u64, num_chunks: *mut u64, memory_usage: *mut u64) -> i32;
+    fn sb200_streaming_matrix_multiply_vector(sm: *const sb200_streaming_matrix, x: *const f64, xlen: u64,
+                                              callback: extern "C" fn(u64, *const f64, u64, *mut c_void) -> i32,
+                                              user: *mut c_void) -> i32;
+    fn sb200_streaming_matrix_free(sm: *mut sb200_streaming_matrix);
     // OptimizedConjugateGradientSolver (src/optimized_solver.rs:168-295)
     fn sb200_cg_config_default(c: *mut sb200_cg_config);
     fn sb200_cg_solve_into(m: *const sb200_matrix, b: *const f64, blen: u64, cfg: *const sb200_cg_config,
