@@ -12,10 +12,13 @@ MODE_CORRECT, the reference's residual-every-5th-iteration cadence).
           around every push launch inside the timed steps) vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline : the oracle's restatement of the reference's rayon row-chunk SpMV (src/simd_ops.rs:202-239) inside
           the same recurrence, all host cores, bounded sample
+  config.parity : the solution of the last timed step (gathered on rank 0 for N > 1) against the oracle's full solve on
+          the same system — bit_exact / max_abs_err / counts_equal — and ||Ax-b||/||b|| from the ORACLE's SpMV
 N > 1 (torchrun, one rank per GPU): STRONG scaling on the same 10 M system — contiguous row blocks, one exchange of
 the term slice + two partial sums per term (sb200_dist_solve: fused peer-memory stores by default,
 SUBLINEAR_B200_DIST=nccl for the allgather + allreduce flavour).
-`--impl reference`: the reference's CPU path (oracle port; no Rust toolchain in this image) on the host cores.
+`--impl reference`: the reference's CPU path (oracle port; no Rust toolchain in this image) on the host cores, timing the
+same step as the GPU arm (one full default solve, row-chunk parallel SpMV on all host threads).
 """
 import argparse
 import json

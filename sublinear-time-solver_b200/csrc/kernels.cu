@@ -8,25 +8,26 @@
 //   EPI_CG    : ap = A p, p.ap                the SpMV + dot of OptimizedConjugateGradientSolver::solve
 //                                            (ref src/optimized_solver.rs:224-232)
 //
-// B200 mapping (HBM / L2-bound sparse gather-reduce; tensor cores are irrelevant here). Three bodies, all of which add
+// B200 mapping (HBM / L2-bound sparse gather-reduce; tensor cores are irrelevant here). Four bodies, all of which add
 // the products of a row LEFT TO RIGHT — the reference's order — with FMA contraction off, so results are bit-identical
 // to CSRStorage::multiply_vector and to each other:
 //   * sell_kernel : SELL-32 copy of the matrix, lane r owns row r of a 32-row block, no shared memory at all
-//                   (the whole 256 KB array serves as L1 for the in-flight gathers); default for vectors <= 48 MB and
-//                   band-local matrices;
+//                   (the whole 256 KB array serves as L1 for the in-flight gathers); default for vectors <= 48 MB,
+//                   band-local matrices and the thin row blocks of the 8-GPU path;
 //   * warp_kernel : CSR slices, coalesced 128/256-bit stream loads by the warp, products transposed through a 1 KB
-//                   warp-private shared-memory chunk; used for ragged / power-law rows and as the body of the
-//   * column-slab passes (launch_tile_kernel): when the gathered vector does not fit the L2 partition of a die, one
-//                   warp_kernel pass per <= 28 MB slab of the vector, the running row sums handed from pass to pass
-//                   (2.4 -> 1.07 L2 sector operations per gather);
-//   * tile_kernel : TMA-staged tile pipeline (cp.async.bulk + mbarrier, LDGSTS gathers), kept selectable
-//                   ($SUBLINEAR_B200_TILE_CFG) as the record of what was measured;
+//                   warp-private shared-memory chunk; used for ragged / power-law rows and the StreamingMatrix chunks;
+//   * slab_kernel : (kernels_slab.cu) when the gathered vector does not fit the L2 partition of a die: ONE persistent
+//                   launch walks <= 28 MB column slabs of the vector, the running row sums carried from slab to slab
+//                   (2.4 -> 1.04 L2 sector operations per gather);
+//   * tile_kernel : (kernels_tile.cu) TMA-staged tile pipeline (cp.async.bulk + mbarrier, LDGSTS gathers), kept
+//                   selectable ($SUBLINEAR_B200_TILE_CFG) as the record of what was measured;
 //   * long_rows_* : grid-wide pre-pass for hub rows (> 1024 entries) of power-law graphs.
 // The stream (values, column indices) is read with L1::no_allocate + L2 evict_first, the gathered vector with L2
 // evict_last (a persisting-L2 set-aside is reserved once per device). The epilogue (diagonal scale, term / solution
-// update, squared norm) is fused; norms are reduced deterministically (fixed-shape tree per CTA or warp, fixed-order
-// sum of the partials by the last CTA) and the last CTA also advances the device-resident loop state (LoopCtl), so the
-// host never has to synchronise per term.
+// update, squared norm, remote stores of the multi-GPU exchange) is fused; norms are reduced deterministically
+// (fixed-shape tree per CTA or warp, fixed-order sum of the partials by the last CTA) and the last CTA also advances the
+// device-resident loop state (LoopCtl) — after consuming the peers' flags in a multi-GPU run — so the host never has to
+// synchronise per term.
 #include <algorithm>
 
 #include "device_util.cuh"
