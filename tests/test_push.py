@@ -249,7 +249,45 @@ def test_oracle_ts_forward_push(oracle):
     assert z.status == O.ERR_NUMERICAL_INSTABILITY
 
 
+FIXTURES = ["jacobi_c1_test_matrix_ones", "jacobi_dd_asymmetric_n50_random", "jacobi_banded_n100_smooth", "jacobi_mcp_3x3"]
+
+
+def _fixture(golden_dir, name):
+    import os
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    n = int(g["n"])
+    return n, g["rows"], g["cols"], g["vals"], g["b"]
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_oracle_ts_forward_push_on_reference_fixtures(oracle, golden_dir, name):
+    """solveForwardPush on the reference's own committed systems (tests/data/test-matrix.json = config C1,
+    scripts/linear_systems/test_matrices, the MCP 3x3 example; stored with the Jacobi golden vectors): converges to A^-1 b"""
+    O = oracle
+    n, rows, cols, vals, b = _fixture(golden_dir, name)
+    A = O.Csr.from_triplets(rows, cols, vals, n, n)
+    r = O.ts_forward_push(A, b, 1e-10, 10_000_000)
+    assert r.converged and r.status == O.OK
+    x = np.linalg.solve(A.to_scipy().toarray(), b)
+    np.testing.assert_allclose(r.solution, x, rtol=0, atol=1e-8)
+    assert np.abs(b - A.multiply_vector(r.solution)).max() < 1e-10 + 1e-13
+
+
 # ---- device path (GPU) -------------------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FIXTURES)
+def test_gpu_forward_push_solve_on_reference_fixtures(oracle, golden_dir, name):
+    O = oracle
+    n, rows, cols, vals, b = _fixture(golden_dir, name)
+    A = O.Csr.from_triplets(rows, cols, vals, n, n)
+    m = sb.SparseMatrix.from_triplets(rows, cols, vals, n, n)
+    r = sb.forward_push_solve(m, b, 1e-10, 10_000_000)
+    o = O.ts_forward_push(A, b, 1e-10, 10_000_000)
+    assert r.converged and o.converged and r.max_residual < 1e-10
+    np.testing.assert_allclose(r.solution, o.solution, rtol=0, atol=1e-8)
+    np.testing.assert_allclose(r.solution, np.linalg.solve(A.to_scipy().toarray(), b), rtol=0, atol=1e-8)
+
 
 @pytest.mark.gpu
 def test_gpu_forward_push_reference_tests(oracle):
