@@ -455,6 +455,13 @@ void sb200_streaming_matrix_free(sb200_streaming_matrix *sm);
 int32_t sb200_solve_entry(const sb200_matrix *m, const double *b, uint64_t blen, const uint64_t *rows,
                           uint64_t nqueries, double eps, uint64_t nwalks, uint64_t max_steps, uint64_t seed,
                           double *est, double *var);
+/* The same batch over several GPUs (replicas): replicas[r] holds the whole matrix on its own device
+ * (sb200_set_device + sb200_matrix_from_* once per GPU); the queries are cut into contiguous slices, one host thread per
+ * replica. Estimates are identical to one sb200_solve_entry call for any number of replicas (the walk keys use the
+ * position in the whole batch). */
+int32_t sb200_solve_entry_replicas(const sb200_matrix *const *replicas, int32_t nreplicas, const double *b, uint64_t blen,
+                                   const uint64_t *rows, uint64_t nqueries, double eps, uint64_t nwalks, uint64_t max_steps,
+                                   uint64_t seed, double *est, double *var);
 /* computePageRank's system (src/core/solver.ts:664-722): S = I - alpha P^T with dangling mass dropped,
  * rhs = (1-alpha)/n.  Edge e: src[e] -> dst[e] with weight w[e] (w NULL = 1). rhs: n doubles (may be NULL). */
 int32_t sb200_pagerank_system(const uint64_t *src, const uint64_t *dst, const double *w, uint64_t nedges,

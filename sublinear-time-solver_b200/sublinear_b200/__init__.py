@@ -213,6 +213,7 @@ def lib():
         "sb200_cg_solve_dev": ([vp, vp, u64, P(_CgConfig), vp, vp, P(_CgResult)], i32),
         "sb200_cg_result_free": ([P(_CgResult)], None),
         "sb200_solve_entry": ([vp, vp, u64, vp, u64, f64, u64, u64, u64, vp, vp], i32),
+        "sb200_solve_entry_replicas": ([vp, C.c_int32, vp, u64, vp, u64, f64, u64, u64, u64, vp, vp], i32),
         "sb200_pagerank_system": ([vp, vp, vp, u64, u64, f64, P(vp), vp], i32),
         "sb200_gen_bench_csr": ([u64, f64, u64, u64, vp, vp, vp, vp, P(u64)], i32),
         "sb200_comm_unique_id": ([vp], i32),
@@ -1044,6 +1045,17 @@ def solve_entry(matrix: SparseMatrix, b, rows, eps=0.01, nwalks=0, max_steps=0, 
     est, var = np.zeros(len(q)), np.zeros(len(q))
     _check(lib().sb200_solve_entry(matrix._h, _ptr(b), len(b), _ptr(q), len(q), eps, nwalks, max_steps, seed,
                                    _ptr(est), _ptr(var)))
+    return est, var
+
+
+def solve_entry_replicas(matrices, b, rows, eps=0.01, nwalks=0, max_steps=0, seed=0):
+    """`solve_entry` over several GPUs: `matrices` = one handle of the same matrix per device. Same estimates as
+    `solve_entry` on one of them."""
+    b, q = _f64(b), _u64(rows)
+    est, var = np.zeros(len(q)), np.zeros(len(q))
+    arr = (C.c_void_p * len(matrices))(*[m._h for m in matrices])
+    _check(lib().sb200_solve_entry_replicas(arr, len(matrices), _ptr(b), len(b), _ptr(q), len(q), eps, nwalks, max_steps,
+                                            seed, _ptr(est), _ptr(var)))
     return est, var
 
 

@@ -460,6 +460,33 @@ def test_pagerank_scaled_c3_properties():
     np.testing.assert_allclose(r.solution, x, rtol=1e-8, atol=1e-15)
 
 
+def test_solve_entry_replicas_match_single_call():
+    """§8e: entry batches are replicas. The dispatcher cuts the batch over the handles (one per GPU; here two handles, on
+    two devices when two are visible) and must return the estimates of one sb200_solve_entry call bit for bit: the walk
+    keys use the position in the whole batch. Errors of a worker thread reach the caller."""
+    n = 50_000
+    rp, ci, v, b = sb.gen_bench_csr(n, 10.0 / n)
+    m0 = sb.SparseMatrix.from_csr(rp, ci, v, n, n)
+    if sb.device_count() > 1:
+        sb.set_device(1)
+    m1 = sb.SparseMatrix.from_csr(rp, ci, v, n, n)
+    sb.set_device(0)
+    rows = np.random.default_rng(3).integers(0, n, 301)
+    est, var = sb.solve_entry(m0, b, rows, eps=0.05, seed=11)
+    for reps in ([m0], [m0, m1], [m0, m1, m0]):
+        e2, v2 = sb.solve_entry_replicas(reps, b, rows, eps=0.05, seed=11)
+        assert np.array_equal(e2, est) and np.array_equal(v2, var), len(reps)
+    e3, _ = sb.solve_entry_replicas([m0, m1], b, rows[:1], eps=0.05, seed=11)      # fewer queries than replicas
+    assert e3[0] == est[0]
+    with pytest.raises(sb.SolverError) as ei:
+        sb.solve_entry_replicas([m0, m1], b, np.array([n + 1]), eps=0.05)
+    assert ei.value.variant == "IndexOutOfBounds"
+    small = sb.SparseMatrix.from_dense(np.eye(3) * 2.0)
+    with pytest.raises(sb.SolverError) as ei:
+        sb.solve_entry_replicas([m0, small], b, rows, eps=0.05)
+    assert ei.value.variant == "InvalidInput"
+
+
 def test_solve_entry_batch_scaled_c4():
     """Config C4 scaled to n = 1 M: 1 024 single-entry queries, eps = 0.01 -> 10 000 walks each (solver.ts:587),
     checked against the full solve within 5 standard errors; same seed -> same estimates."""
