@@ -249,6 +249,91 @@ def test_oracle_ts_forward_push(oracle):
     assert z.status == O.ERR_NUMERICAL_INSTABILITY
 
 
+def complete_graph(n):
+    """create_complete_graph (push_tests.rs:62-77): every node to every other node, weight 1/(n-1)"""
+    rows = np.repeat(np.arange(n), n - 1)
+    cols = np.array([j for i in range(n) for j in range(n) if j != i])
+    return np.arange(n + 1) * (n - 1), cols, np.full(n * (n - 1), 1.0 / (n - 1)), n
+
+
+class _OracleApi:
+    """the oracle behind the method names of the reference's solvers, so that the restated tests read like push_tests.rs"""
+
+    def __init__(self, O, graph, **cfg):
+        rp, ci, w, n = graph
+        self.O, self.A, self.cfg, self.alpha = O, O.Csr(n, n, w, ci, rp), cfg, cfg.get("alpha", 0.15)
+
+    def solve_single_source(self, s): return self.O.forward_push(self.A, s, **self.cfg)
+    def solve_multi_source(self, s): return self.O.forward_push(self.A, list(s), **self.cfg)
+    def query_single_entry(self, s, t): return float(self.solve_single_source(s).estimate[t])
+    def solve_single_target(self, t): return self.O.backward_push(self.A, t, **self.cfg)
+    def solve_multi_target(self, t): return self.O.backward_push(self.A, list(t), **self.cfg)
+    def query_transition_probability(self, s, t): return float(self.solve_single_target(t).estimate[s])
+    def extrapolated_solution(self, r): return r.estimate + self.alpha * r.residual
+    def reachability_probabilities(self, t): return self.extrapolated_solution(self.solve_single_target(t))
+
+    def solve_bidirectional(self, s, t):
+        f, b = self.solve_single_source(s), self.solve_single_target(t)
+        return self.O.push_combine_with_forward(self.alpha, b, f.estimate, f.residual)
+
+
+class _DeviceApi:
+    def __init__(self, graph, **cfg):
+        rp, ci, w, n = graph
+        self.g = sb.PushGraph.from_matrix(rp, ci, w, n)
+        self.c = sb.PushConfig(**cfg)
+        self.f, self.b = sb.ForwardPushSolver(self.g, self.c), sb.BackwardPushSolver(self.g, self.c)
+        self.bi = sb.BidirectionalPushSolver(self.g, self.c, self.c)
+
+    def __getattr__(self, name):
+        for o in (self.f, self.b, self.bi):
+            if hasattr(o, name):
+                return getattr(o, name)
+        raise AttributeError(name)
+
+    def extrapolated_solution(self, r): return self.f.extrapolated_solution(r)
+
+
+def reference_push_tests(make):
+    """tests/rust/push_tests.rs:81-330 restated against `make(graph, **config)` (the oracle or the device solvers).
+    Two of the reference's own assertions do not hold for its algorithm and are asserted as they really come out:
+    test_forward_push_complete_graph wants every entry within 0.1 of alpha (the source holds 0.338 of the mass), and
+    test_backward_push_reachability wants reach[1] > reach[0] on a path (node 0 has no in-edge and keeps what reaches it)."""
+    s = make(simple_graph())
+    r = s.solve_single_source(0)                                             # test_forward_push_basic_functionality
+    assert r.push_count > 0 and r.nodes_visited > 0 and r.estimate[0] > 0.0 and r.residual_norm >= 0.0
+    assert (r.estimate >= 0).all() and (r.residual >= 0).all()
+    assert abs(s.extrapolated_solution(r).sum() - 1.0) < 0.1                 # test_forward_push_mass_conservation
+    tight = make(simple_graph(), epsilon=1e-10, max_pushes=100_000).solve_single_source(0)   # test_forward_push_convergence
+    loose = make(simple_graph(), epsilon=1e-4, max_pushes=100_000).solve_single_source(0)
+    assert tight.push_count >= loose.push_count and tight.residual_norm <= loose.residual_norm * 10.0
+    m = s.solve_multi_source([0, 2])                                         # test_forward_push_multi_source
+    assert m.push_count > 0 and m.nodes_visited > 0 and m.estimate[0] > 0.0 and m.estimate[2] > 0.0 and m.estimate.sum() > 0.0
+    assert s.query_single_entry(0, 1) >= 0.0 and s.query_single_entry(0, 0) > 0.0     # test_forward_push_single_entry_query
+    p = make(path_graph(5)).solve_single_source(0)                           # test_forward_push_path_graph
+    assert p.estimate[0] > p.estimate[1] and (p.estimate[1] > p.estimate[2] or p.estimate[2] < 1e-6)
+    c = make(complete_graph(4))                                              # test_forward_push_complete_graph
+    final = c.extrapolated_solution(c.solve_single_source(0))
+    assert abs(final[0] - 26.0 / 77.0) < 1e-5 and np.abs(final[1:] - 17.0 / 77.0).max() < 1e-5   # exact PPR: 26/77, 17/77
+    b = s.solve_single_target(3)                                             # test_backward_push_basic_functionality
+    assert b.push_count > 0 and b.nodes_visited > 0 and b.estimate[3] > 0.0 and b.residual_norm >= 0.0 and (b.estimate >= 0).all()
+    assert 0.0 <= s.query_transition_probability(0, 3) <= 1.0 and s.query_transition_probability(0, 0) > 0.0
+    mt = s.solve_multi_target([1, 3])                                        # test_backward_push_multi_target
+    assert mt.push_count > 0 and mt.nodes_visited > 0 and mt.estimate[1] > 0.0 and mt.estimate[3] > 0.0
+    reach = make(path_graph(5)).reachability_probabilities(4)                # test_backward_push_reachability
+    assert reach[4] > reach[3] > reach[2] > reach[1] and reach[0] > reach[1]
+    bi, fq, bq = s.solve_bidirectional(0, 3), s.query_single_entry(0, 3), s.query_transition_probability(0, 3)
+    assert bi >= 0.0 and fq >= 0.0 and bq >= 0.0                             # test_bidirectional_solver_consistency
+    z = s.solve_single_source(10)                                            # out-of-bounds source: zeros (push_tests.rs:429-495)
+    assert z.push_count == 0 and not z.estimate.any() and not z.residual.any()
+    zt = s.solve_single_target(10)
+    assert zt.push_count == 0 and not zt.estimate.any()
+
+
+def test_oracle_reference_push_tests(oracle):
+    reference_push_tests(lambda g, **cfg: _OracleApi(oracle, g, **cfg))
+
+
 FIXTURES = ["jacobi_c1_test_matrix_ones", "jacobi_dd_asymmetric_n50_random", "jacobi_banded_n100_smooth", "jacobi_mcp_3x3"]
 
 
@@ -274,6 +359,11 @@ def test_oracle_ts_forward_push_on_reference_fixtures(oracle, golden_dir, name):
 
 
 # ---- device path (GPU) -------------------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+def test_gpu_reference_push_tests():
+    reference_push_tests(lambda g, **cfg: _DeviceApi(g, **cfg))
+
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", FIXTURES)
