@@ -160,9 +160,12 @@ double orc_push_iterations(const orc_csr *m, const double *b, uint64_t nterms, i
  * `adj` is the adjacency CSR (row u = out-edges of u with weights); degrees are row sums, reverse degrees column sums.
  * Pop order: WorkItem only derives PartialOrd (src/graph/mod.rs:141-147) and has no Ord impl, so BinaryHeap<WorkItem>
  * does not compile in the reference; the restatement orders items by (priority, node_id), what the derive would give.
- * PARITY UNPINNED for this path: the reference holds no golden vectors for it and its own source does not fix a pop
- * order; the restatement is held to the properties the reference's tests assert (mass, positivity, counts > 0) and to
- * the exact personalised PageRank (tests/test_push.py). est / res: n doubles each. */
+ * Pinning: the reference holds no golden vectors for this path and cannot be built (no Ord impl, no Rust toolchain
+ * here), but (priority, node_id) is a TOTAL order, so the pop sequence does not depend on the heap's internals: the
+ * restatement is pinned bit for bit to an independent pure-Python restatement (tests/test_push.py::py_forward_push,
+ * heapq) on the graphs of tests/rust/push_tests.rs:15-59, with the vectors committed (tests/golden/push_*.npz,
+ * make_golden_push.py), and held to the reference's own tests restated (reference_push_tests) and to the exact
+ * personalised PageRank. Not pinned to an output of reference code: none exists. est / res: n doubles each. */
 typedef struct {
     double alpha;            /* 0.15 */
     double epsilon;          /* 1e-6 */
